@@ -1,0 +1,22 @@
+"""audio_denoising_b200 -- B200 (sm_100a) implementation of the belacks/audio-denoising inference hot path.
+
+waveform -> STFT -> Mel log-magnitude -> GRUUNet2 -> inverse Mel -> Griffin-Lim -> iSTFT/OLA, as hand-written
+CUDA kernels in ``libb200denoise.so`` (C-ABI: ``include/b200denoise.h``) behind the reference's own Python
+interfaces: ``GRUUNet2`` (gruunet2.py), the five torchaudio-style transforms the reference constructs
+(app3.py:135-153), and the ``utils`` names.  CUDA only; the package raises if the library is missing.
+"""
+from . import _cabi
+from .gruunet2 import GRUUNet2
+from .pipeline import DenoisePipeline, StreamingDenoiser
+from .transforms import GriffinLim, InverseMelScale, InverseSpectrogram, MelScale, Spectrogram
+
+__all__ = [
+    "GRUUNet2", "Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram",
+    "DenoisePipeline", "StreamingDenoiser", "native_library",
+]
+__version__ = "0.1.0"
+
+
+def native_library():
+    """Load libb200denoise.so (raises ImportError when it has not been built)."""
+    return _cabi.lib()

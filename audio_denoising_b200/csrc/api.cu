@@ -1,0 +1,397 @@
+// api.cu -- extern "C" surface of libb200denoise.so (declared in include/b200denoise.h).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace b2d {
+
+std::atomic<unsigned long long> g_launches{0};
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int model_pack(b2d_model* m, const float* const* hp, const float* const* offs);  // model.cu
+bool model_config_supported(const b2d_model_config* c);
+int model_pack_tc(b2d_model* m);  // conv_tc.cu
+int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
+                     const float2* init_angles, int n_iter, float momentum, int conv_mode, float* out, void* ws,
+                     size_t ws_bytes, cudaStream_t st);  // stream.cu
+size_t stream_step_ws(const b2d_plan* p, const b2d_model* m, int S);
+
+static bool factor(int M, FftDesc& fd) {
+  fd.M = M;
+  fd.npass = 0;
+  int m = M;
+  const int radices[5] = {8, 4, 2, 3, 5};
+  for (int r : radices) {
+    while (m % r == 0 && m > 1) {
+      if (fd.npass >= kMaxPass) return false;
+      fd.radix[fd.npass++] = r;
+      m /= r;
+    }
+  }
+  return m == 1;
+}
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+  B2D_CUDA(cudaMalloc(dst, v.size() * sizeof(T)));
+  B2D_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return B2D_OK;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" {
+
+int b2d_version(void) { return 100; }
+const char* b2d_last_error_string(void) { return last_error().c_str(); }
+unsigned long long b2d_launch_count(void) { return g_launches.load(); }
+
+int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, b2d_plan** out) {
+  B2D_REQUIRE(out != nullptr, B2D_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  B2D_REQUIRE(n_fft >= 64 && n_fft <= 4096 && n_fft % 4 == 0, B2D_ERR_UNSUPPORTED,
+              "n_fft must be a multiple of 4 in [64, 4096] (got %d)", n_fft);
+  B2D_REQUIRE(hop >= 1 && hop <= n_fft, B2D_ERR_BAD_ARG, "hop must be in [1, n_fft] (got %d)", hop);
+  B2D_REQUIRE(n_mels >= 1 && n_mels <= 256, B2D_ERR_UNSUPPORTED, "n_mels must be in [1, 256] (got %d)", n_mels);
+  B2D_REQUIRE(h_mel_fb != nullptr && h_pinv != nullptr, B2D_ERR_BAD_ARG, "filterbank / pinv pointers are NULL");
+  FftDesc fd;
+  B2D_REQUIRE(factor(n_fft / 2, fd), B2D_ERR_UNSUPPORTED, "n_fft/2 = %d is not of the form 2^a 3^b 5^c", n_fft / 2);
+
+  b2d_plan* p = new b2d_plan();
+  memset(p, 0, sizeof(*p));
+  p->n_fft = n_fft; p->hop = hop; p->n_mels = n_mels;
+  p->M = n_fft / 2; p->F = p->M + 1; p->Fp = p->M + 4; p->fft = fd;
+  B2D_CUDA(cudaGetDevice(&p->device));
+  B2D_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  const int N = n_fft, M = p->M, F = p->F;
+  std::vector<float2> tw(M), rtw(M / 2 + 1);
+  for (int k = 0; k < M; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)M;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  for (int k = 0; k <= M / 2; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)N;
+    rtw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  std::vector<float> win(N), winn(N), inv_env(hop);
+  for (int n = 0; n < N; ++n) {
+    // torch.hann_window(N, periodic=True) evaluated in float32 like torch does (0.5 - 0.5 cos)
+    const float w = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)N));
+    win[n] = w;
+    winn[n] = w / (float)N;
+  }
+  for (int i = 0; i < hop; ++i) {
+    float e = 0.f;
+    for (int n = i; n < N; n += hop) e += win[n] * win[n];
+    inv_env[i] = 1.0f / e;
+  }
+  // compact mel columns
+  std::vector<int> lo(n_mels), cnt(n_mels), off(n_mels);
+  std::vector<float> mw;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int f = 0; f < F; ++f)
+      if (h_mel_fb[(size_t)f * n_mels + m] != 0.f) {
+        if (first < 0) first = f;
+        last = f;
+      }
+    if (first < 0) { first = 0; last = -1; }
+    lo[m] = first; cnt[m] = last - first + 1; off[m] = (int)mw.size();
+    for (int f = first; f <= last; ++f) mw.push_back(h_mel_fb[(size_t)f * n_mels + m]);
+  }
+  if (mw.empty()) mw.push_back(0.f);
+  p->mel_nnz = (int)mw.size();
+  std::vector<float> pinv((size_t)p->Fp * n_mels, 0.f);
+  memcpy(pinv.data(), h_pinv, sizeof(float) * (size_t)F * n_mels);
+  int rc;
+  if ((rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_rtw, rtw)) || (rc = upload(&p->d_win, win)) ||
+      (rc = upload(&p->d_winn, winn)) || (rc = upload(&p->d_inv_env, inv_env)) || (rc = upload(&p->d_mel_lo, lo)) ||
+      (rc = upload(&p->d_mel_cnt, cnt)) || (rc = upload(&p->d_mel_off, off)) || (rc = upload(&p->d_mel_w, mw)) ||
+      (rc = upload(&p->d_pinv, pinv))) {
+    b2d_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return B2D_OK;
+}
+
+void b2d_plan_destroy(b2d_plan* p) {
+  if (!p) return;
+  cudaFree(p->d_tw); cudaFree(p->d_rtw); cudaFree(p->d_win); cudaFree(p->d_winn); cudaFree(p->d_inv_env);
+  cudaFree(p->d_mel_lo); cudaFree(p->d_mel_cnt); cudaFree(p->d_mel_off); cudaFree(p->d_mel_w); cudaFree(p->d_pinv);
+  cudaFree(p->d_tw8);
+  delete p;
+}
+int b2d_plan_num_frames(const b2d_plan* p, int L) { return p ? 1 + L / p->hop : B2D_ERR_BAD_ARG; }
+int b2d_plan_output_length(const b2d_plan* p, int T) { return p ? p->hop * (T - 1) : B2D_ERR_BAD_ARG; }
+int b2d_plan_frame_stride(const b2d_plan* p) { return p ? p->Fp : B2D_ERR_BAD_ARG; }
+
+int b2d_model_create(const b2d_model_config* cfg, const float* const* h_params, int n_params,
+                     const float* const* h_gs_offsets, b2d_model** out) {
+  B2D_REQUIRE(out != nullptr && cfg != nullptr && h_params != nullptr && h_gs_offsets != nullptr, B2D_ERR_BAD_ARG, "NULL argument");
+  *out = nullptr;
+  B2D_REQUIRE(model_config_supported(cfg), B2D_ERR_UNSUPPORTED,
+              "GRUUNet2 config not supported by the kernels: need hidden=17 x4 levels, bins=4, k=3, s=2, p=1 "
+              "(got hidden=%d levels=%d bins=%d k=%d s=%d p=%d G=%d)",
+              cfg->hidden, cfg->levels, cfg->num_compressed_bins, cfg->kernel, cfg->stride, cfg->padding, cfg->num_gaussians);
+  B2D_REQUIRE(n_params == 4 * cfg->levels + 2, B2D_ERR_BAD_ARG, "expected %d parameter tensors, got %d", 4 * cfg->levels + 2, n_params);
+  for (int i = 0; i < n_params; ++i) B2D_REQUIRE(h_params[i] != nullptr, B2D_ERR_BAD_ARG, "parameter %d is NULL", i);
+  for (int i = 0; i < 3; ++i) B2D_REQUIRE(h_gs_offsets[i] != nullptr, B2D_ERR_BAD_ARG, "gs.offset %d is NULL", i);
+  b2d_model* m = new b2d_model();
+  memset(m, 0, sizeof(*m));
+  m->cfg = *cfg;
+  m->n_mels = cfg->num_compressed_bins << cfg->levels;
+  B2D_CUDA(cudaGetDevice(&m->device));
+  int rc = model_pack(m, h_params, h_gs_offsets);
+  if (rc == B2D_OK) rc = model_pack_tc(m);
+  if (rc != B2D_OK) {
+    b2d_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return B2D_OK;
+}
+void b2d_model_destroy(b2d_model* m) {
+  if (!m) return;
+  cudaFree(m->d_blob);
+  cudaFree(m->d_tc);
+  delete m;
+}
+int b2d_model_n_mels(const b2d_model* m) { return m ? m->n_mels : B2D_ERR_BAD_ARG; }
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define CHECK_BATCH(B) B2D_REQUIRE((B) >= 1 && (B) <= 65535, B2D_ERR_BAD_ARG, "batch must be in [1, 65535] per call (got %d)", (B))
+
+int b2d_peak(const float* wave, int B, int L, float* peak, void* stream) {
+  B2D_REQUIRE(wave && peak, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(L >= 1, B2D_ERR_BAD_ARG, "L must be >= 1");
+  // single-pass variant: one block per clip (partial buffer = peak itself)
+  return launch_peak(wave, B, L, peak, peak, 1, ST(stream));
+}
+
+static int check_stft_args(const b2d_plan* plan, const float* wave, int B, int L) {
+  B2D_REQUIRE(plan && wave, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(L > plan->n_fft / 2, B2D_ERR_BAD_ARG,
+              "reflect padding needs L > n_fft/2 (L=%d, n_fft=%d) -- same restriction as torch.stft", L, plan->n_fft);
+  return B2D_OK;
+}
+
+int b2d_stft(const b2d_plan* plan, const float* wave, int B, int L, b2d_c64* spec, void* stream) {
+  int rc = check_stft_args(plan, wave, B, L);
+  if (rc) return rc;
+  B2D_REQUIRE(spec, B2D_ERR_BAD_ARG, "spec is NULL");
+  return launch_stft(plan, wave, nullptr, B, L, nullptr, nullptr, reinterpret_cast<float2*>(spec), ST(stream));
+}
+
+int b2d_stft_mel_log1p(const b2d_plan* plan, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
+                       float* logmel_bm, b2d_c64* spec, void* stream) {
+  int rc = check_stft_args(plan, wave, B, L);
+  if (rc) return rc;
+  B2D_REQUIRE(logmel_bt || logmel_bm || spec, B2D_ERR_BAD_ARG, "all outputs are NULL");
+  return launch_stft(plan, wave, inv_scale, B, L, logmel_bt, logmel_bm, reinterpret_cast<float2*>(spec), ST(stream));
+}
+
+int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* mel, void* stream) {
+  B2D_REQUIRE(plan && mag && mel, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(T >= 1, B2D_ERR_BAD_ARG, "T must be >= 1");
+  return launch_mel_scale(plan, mag, B, T, mel, ST(stream));
+}
+
+size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T) {
+  if (!model || B < 1 || T < 1) return 0;
+  return model_workspace_bytes(model, B, T);
+}
+int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T, int conv_mode,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  B2D_REQUIRE(model && x && hx && out, B2D_ERR_BAD_ARG, "NULL pointer");
+  return model_forward(model, x, hx, out, nullptr, 0, 0.f, B, T, conv_mode, workspace, workspace_bytes, ST(stream));
+}
+
+int b2d_residual_mel(const float* x, const float* pred, float* mel_bt, size_t n, int mode, float out_scale, void* stream) {
+  B2D_REQUIRE(x && pred && mel_bt, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(mode == 0 || mode == 1, B2D_ERR_BAD_ARG, "mode must be 0 (app) or 1 (server)");
+  if (n == 0) return B2D_OK;
+  return launch_residual(x, pred, mel_bt, n, mode, out_scale, ST(stream));
+}
+
+int b2d_inverse_mel(const b2d_plan* plan, const float* mel, int B, int T, float* lin, void* stream) {
+  B2D_REQUIRE(plan && mel && lin, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(T >= 1, B2D_ERR_BAD_ARG, "T must be >= 1");
+  return launch_inverse_mel(plan, mel, B, T, lin, true, ST(stream));
+}
+int b2d_inverse_mel_frames(const b2d_plan* plan, const float* mel_bt, int B, int T, float* mag_tf, void* stream) {
+  B2D_REQUIRE(plan && mel_bt && mag_tf, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "B and T must be >= 1");
+  B2D_REQUIRE(aligned16(mag_tf), B2D_ERR_ALIGN, "mag_tf must be 16-byte aligned");
+  return launch_inverse_mel(plan, mel_bt, B, T, mag_tf, false, ST(stream));
+}
+
+size_t b2d_griffinlim_workspace_bytes(const b2d_plan* plan, int B, int T) {
+  if (!plan || B < 1 || T < 3) return 0;
+  return gl_workspace_bytes(plan, B, T, true);
+}
+int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, int B, int T, int n_iter,
+                          float momentum, const float* out_scale, float* wave, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  B2D_REQUIRE(plan && mag_tf && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(aligned16(mag_tf) && aligned16(workspace), B2D_ERR_ALIGN, "mag_tf / workspace must be 16-byte aligned");
+  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, out_scale, wave, workspace,
+                workspace_bytes, ST(stream));
+}
+int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, int B, int T, int n_iter, float momentum,
+                   const float* out_scale, float* wave, void* workspace, size_t workspace_bytes, void* stream) {
+  B2D_REQUIRE(plan && mag && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
+  B2D_REQUIRE(aligned16(workspace), B2D_ERR_ALIGN, "workspace must be 16-byte aligned");
+  B2D_REQUIRE(workspace_bytes >= gl_workspace_bytes(plan, B, T, true), B2D_ERR_WORKSPACE, "Griffin-Lim workspace too small");
+  const size_t core = gl_workspace_bytes(plan, B, T, false);
+  float* mag_tf = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + core);
+  int rc = launch_to_frame_layout(mag, mag_tf, B, plan->F, T, plan->Fp, ST(stream));
+  if (rc) return rc;
+  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, out_scale, wave, workspace,
+                core, ST(stream));
+}
+
+int b2d_istft(const b2d_plan* plan, const b2d_c64* spec, const float* mag, int B, int T, float* wave, void* stream) {
+  B2D_REQUIRE(plan && spec && wave, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(plan->hop * 2 == plan->n_fft, B2D_ERR_UNSUPPORTED, "iSTFT requires hop == n_fft/2 (got n_fft=%d hop=%d)", plan->n_fft, plan->hop);
+  B2D_REQUIRE(T >= 2, B2D_ERR_BAD_ARG, "iSTFT needs at least 2 frames");
+  return launch_istft(plan, reinterpret_cast<const float2*>(spec), mag, B, T, wave, ST(stream));
+}
+
+// ---- whole chains -----------------------------------------------------------------------------
+// workspace: peak[B] | logmel[B,T,M] | pred[B,T,M] | mel[B,T,M] | mag_tf[B,T,Fp] | model ws | GL ws
+struct ChainWs {
+  float *peak, *logmel, *pred, *mel, *mag;
+  unsigned char* model_ws; size_t model_bytes;
+  unsigned char* gl_ws; size_t gl_bytes;
+  size_t total;
+};
+static ChainWs chain_layout(const b2d_plan* p, const b2d_model* m, int B, int T, void* base, bool with_gl, bool with_spec) {
+  ChainWs w;
+  unsigned char* q = static_cast<unsigned char*>(base);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return q ? q + at : nullptr; };
+  const size_t nm = (size_t)B * T * p->n_mels * sizeof(float);
+  w.peak = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
+  w.logmel = reinterpret_cast<float*>(take(nm));
+  w.pred = reinterpret_cast<float*>(take(nm));
+  w.mel = reinterpret_cast<float*>(take(nm));
+  w.mag = reinterpret_cast<float*>(take(with_spec ? (size_t)B * p->F * T * sizeof(float) : (size_t)B * T * p->Fp * sizeof(float)));
+  w.model_bytes = model_workspace_bytes(m, B, T);
+  w.model_ws = take(w.model_bytes);
+  if (with_gl) {
+    w.gl_bytes = gl_workspace_bytes(p, B, T, false);
+    w.gl_ws = take(w.gl_bytes);
+  } else {  // noisy-phase chain keeps the complex spectrogram instead
+    w.gl_bytes = (size_t)B * p->F * T * sizeof(float2);
+    w.gl_ws = take(w.gl_bytes);
+  }
+  w.total = o;
+  return w;
+}
+
+size_t b2d_denoise_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L) {
+  if (!plan || !model || B < 1 || L <= plan->n_fft / 2) return 0;
+  const int T = 1 + L / plan->hop;
+  if (T < 3) return 0;
+  return chain_layout(plan, model, B, T, nullptr, true, false).total;
+}
+
+int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L, float* hx,
+                      const b2d_c64* init_angles, int n_iter, float momentum, int normalise, int conv_mode, float* wave,
+                      float* logmel_bt, float* pred_bt, float* mag_tf, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_stft_args(plan, noisy, B, L);
+  if (rc) return rc;
+  B2D_REQUIRE(model && hx && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(model->n_mels == plan->n_mels, B2D_ERR_BAD_ARG, "plan n_mels (%d) != model n_mels (%d)", plan->n_mels, model->n_mels);
+  B2D_REQUIRE(aligned16(workspace), B2D_ERR_ALIGN, "workspace must be 16-byte aligned");
+  const int T = 1 + L / plan->hop;
+  B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "clip too short: need at least 3 frames");
+  const ChainWs w = chain_layout(plan, model, B, T, workspace, true, false);
+  B2D_REQUIRE(workspace_bytes >= w.total, B2D_ERR_WORKSPACE, "denoise workspace too small (%zu < %zu)", workspace_bytes, w.total);
+  cudaStream_t st = ST(stream);
+  float* logmel = logmel_bt ? logmel_bt : w.logmel;
+  float* pred = pred_bt ? pred_bt : w.pred;
+  float* mag = mag_tf ? mag_tf : w.mag;
+  if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak, 1, st))) return rc;
+  if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
+  if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
+  if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) return rc;
+  return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, normalise ? w.peak : nullptr, wave,
+                w.gl_ws, w.gl_bytes, st);
+}
+
+size_t b2d_denoise_noisy_phase_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L) {
+  if (!plan || !model || B < 1 || L <= plan->n_fft / 2) return 0;
+  const int T = 1 + L / plan->hop;
+  return chain_layout(plan, model, B, T, nullptr, false, true).total;
+}
+
+int b2d_denoise_noisy_phase(const b2d_plan* plan, const b2d_model* model, const float* x, int B, int L, float* hx,
+                            float out_scale, float hx_decay, int conv_mode, float* wave, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  int rc = check_stft_args(plan, x, B, L);
+  if (rc) return rc;
+  B2D_REQUIRE(model && hx && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(model->n_mels == plan->n_mels, B2D_ERR_BAD_ARG, "plan n_mels (%d) != model n_mels (%d)", plan->n_mels, model->n_mels);
+  B2D_REQUIRE(plan->hop * 2 == plan->n_fft, B2D_ERR_UNSUPPORTED, "iSTFT requires hop == n_fft/2");
+  const int T = 1 + L / plan->hop;
+  B2D_REQUIRE(T >= 2, B2D_ERR_BAD_ARG, "clip too short: need at least 2 frames");
+  const ChainWs w = chain_layout(plan, model, B, T, workspace, false, true);
+  B2D_REQUIRE(workspace_bytes >= w.total, B2D_ERR_WORKSPACE, "workspace too small (%zu < %zu)", workspace_bytes, w.total);
+  cudaStream_t st = ST(stream);
+  float2* spec = reinterpret_cast<float2*>(w.gl_ws);
+  if ((rc = launch_stft(plan, x, nullptr, B, L, w.logmel, nullptr, spec, st))) return rc;
+  if ((rc = model_forward(model, w.logmel, hx, w.pred, w.mel, 2, out_scale, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
+  // server.py:215 feeds [B, n_mels, T]; the frame-layout GEMM needs [B,T,n_mels] -> out torch layout via strided kernel
+  // (mel is [B,T,n_mels]; produce lin [B,F,T] with the torch-layout kernel after a transpose-free trick: we use the
+  //  frame-layout kernel into a [B,T,Fp] buffer and let the iSTFT read magnitudes from it through a transposed view.)
+  // Simpler and cheap: reuse to-torch conversion by running the torch-layout GEMM on a transposed copy of mel.
+  // mel_bm = w.pred reused as scratch [B, n_mels, T].
+  {
+    // transpose [B,T,n_mels] -> [B,n_mels,T] with the generic tile transpose (F := T rows, T := n_mels cols)
+    if ((rc = launch_to_frame_layout(w.mel, w.pred, B, T, plan->n_mels, T, st))) return rc;
+  }
+  if ((rc = launch_inverse_mel(plan, w.pred, B, T, w.mag, true, st))) return rc;
+  if ((rc = launch_istft(plan, spec, w.mag, B, T, wave, st))) return rc;
+  return scale_inplace(hx, (size_t)B * model->cfg.hidden * model->cfg.num_compressed_bins, hx_decay, st);
+}
+
+size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int S) {
+  if (!plan || !model || S < 1) return 0;
+  return stream_step_ws(plan, model, S);
+}
+int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx, float* ola,
+                    const b2d_c64* init_angles, int n_iter, float momentum, int conv_mode, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  B2D_REQUIRE(plan && model && chunk && hx && ola && out && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  return stream_step_impl(plan, model, chunk, S, hx, ola, reinterpret_cast<const float2*>(init_angles), n_iter, momentum,
+                          conv_mode, out, workspace, workspace_bytes, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// common.cuh -- shared host/device helpers for libb200denoise (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/b200denoise.h"
+
+namespace b2d {
+
+// ---- error plumbing -------------------------------------------------------------------------
+std::string& last_error();                  // thread-local
+int fail(int code, const char* fmt, ...);   // records message, returns code
+extern std::atomic<unsigned long long> g_launches;
+
+#define B2D_REQUIRE(cond, code, ...)                   \
+  do {                                                 \
+    if (!(cond)) return ::b2d::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define B2D_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::b2d::fail(B2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                         __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// after every kernel launch
+#define B2D_LAUNCH_CHECK(name)                                                                    \
+  do {                                                                                            \
+    ::b2d::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::b2d::fail(B2D_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- plan / model (host structs; device tables owned by them) -------------------------------
+constexpr int kMaxPass = 8;
+
+struct FftDesc {  // passed by value to kernels
+  int M;          // complex length = n_fft / 2
+  int npass;
+  int radix[kMaxPass];
+};
+
+}  // namespace b2d
+
+struct b2d_plan {
+  int n_fft, hop, n_mels, F, M, Fp;
+  b2d::FftDesc fft;
+  int device;
+  int num_sms;
+  float2* d_tw;       // [M]      W_M^k   = exp(-2 pi i k / M)
+  float2* d_rtw;      // [M/2+1]  W_N^k   = exp(-2 pi i k / N)   (real-FFT split twiddles)
+  float* d_win;       // [N]      periodic Hann
+  float* d_winn;      // [N]      Hann / N (synthesis window with the irfft 1/N folded in)
+  float* d_inv_env;   // [hop]    1 / (w^2[i] + w^2[i+hop])      (valid when hop == N/2)
+  int* d_mel_lo;      // [n_mels] first frequency bin with non-zero weight
+  int* d_mel_cnt;     // [n_mels] number of consecutive bins
+  int* d_mel_off;     // [n_mels] offset into d_mel_w
+  float* d_mel_w;     // compact column weights
+  int mel_nnz;
+  float* d_pinv;      // [Fp, n_mels] rows F..Fp-1 zero
+  float2* d_tw8;      // fast path tables (see gl_fast.cuh), may be null
+};
+
+struct b2d_model {
+  b2d_model_config cfg;
+  int n_mels;
+  int device;
+  float* d_blob;      // all packed tensors, one allocation
+  size_t blob_floats;
+  // offsets (in floats) into d_blob, see model.cu
+  int enc_w[6], enc_pb[6];
+  int rec_w, rec_pb;
+  int dec_w[6], dec_pb[6];
+  // bf16 operand images for the tcgen05 path (hi / lo split), see conv_tc.cu
+  void* d_tc;
+  size_t tc_bytes;
+  int tc_off[32];
+};

@@ -1,0 +1,275 @@
+// griffinlim.cu -- K6: fused fast Griffin-Lim iteration (TA:functional/functional.py:255-353).
+//
+// One launch = one iteration.  The launch reads the current time-domain iterate x_k, and per frame
+//   rebuilt = rfft(window * x_k)                      (torch.stft, center/reflect)
+//   a       = rebuilt - m * tprev ; a /= |a| + 1e-16  (momentum + projection to unit modulus)
+//   tprev   = rebuilt                                 (in place; each frame has one owner)
+//   y       = irfft(mag * a) * window                 (torch.istft, first half)
+// and overlap-adds y into x_{k+1}.  `angles` is never materialised.  Algorithmic HBM bytes per
+// iteration per clip: read x (4 L), read tprev (8 F T), read mag (4 F T), write tprev (8 F T),
+// write x (4 L) = 20 F T + 8 L  (SURVEY.md section 8d).
+//
+// The iterate x is kept in a "partial hop-block" format so that no CTA ever needs another CTA's
+// frames and no atomics are used: a clip's T frames are cut into R runs of n frames; run r owns
+// n+1 hop-blocks, slot c holding  [second half of frame r*n+c-1] + [first half of frame r*n+c]
+// restricted to the frames of that run.  A hop-block on a run boundary is the sum of two slots
+// (x_block_sample).  The window-envelope division and the reflect padding of torch.stft are applied
+// when the next iteration stages its input.
+#include "fft.cuh"
+#include "kernels.cuh"
+
+namespace b2d {
+
+struct GlArgs {
+  const float* mag_tf;    // [B,T,Fp]
+  const float2* angles0;  // [B,F,T] torch layout or null (init only)
+  float2* tprev;          // [B,T,M]   slot 0 = (Re X[0], Re X[M])
+  const float* xin;       // partial hop-block format
+  float* xout;            // partial hop-block format
+  int B, T, n, R, G;
+  int n_fft, hop, M, F, Fp;
+  FftDesc fd;
+  const float2* tw;
+  const float2* rtw;
+  const float* win;
+  const float* winn;
+  const float* inv_env;
+  float mom;
+  int init, use_prev, store_prev;
+};
+
+// normalised interior hop-block sample, 1 <= j <= T-1
+__device__ __forceinline__ float x_block_sample(const float* __restrict__ part, const float* __restrict__ inv_env,
+                                                int b, int R, int n, int hop, int j, int i) {
+  const int r1 = (j - 1) / n, r2 = j / n;
+  float v = part[((size_t)(b * R + r1) * (n + 1) + (j - r1 * n)) * hop + i];
+  if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * hop + i];
+  return v * inv_env[i];
+}
+// sample i of padded hop-block j (0 <= j <= T) of the reflect-padded iterate
+__device__ __forceinline__ float x_padded(const float* __restrict__ part, const float* __restrict__ inv_env, int b,
+                                          int R, int n, int hop, int T, int j, int i) {
+  if (j == 0) return (i == 0) ? x_block_sample(part, inv_env, b, R, n, hop, 2, 0)
+                              : x_block_sample(part, inv_env, b, R, n, hop, 1, hop - i);
+  if (j == T) return (i == hop - 1) ? x_block_sample(part, inv_env, b, R, n, hop, T - 2, hop - 1)
+                                    : x_block_sample(part, inv_env, b, R, n, hop, T - 1, hop - 2 - i);
+  return x_block_sample(part, inv_env, b, R, n, hop, j, i);
+}
+
+__device__ __forceinline__ float2 unit_dir(float2 a) {
+  const float inv = 1.0f / (sqrtf(a.x * a.x + a.y * a.y) + 1e-16f);
+  return make_float2(a.x * inv, a.y * inv);
+}
+
+__global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = a.M, N = a.n_fft, G = a.G, hop = a.hop, n = a.n, R = a.R, T = a.T;
+  float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+  float2* bufA = tw_s + M;
+  float2* bufB = bufA + G * M;
+  float* xin_s = reinterpret_cast<float*>(bufB + G * M);  // (G+1)*hop
+  float* carry_s = xin_s + (G + 1) * hop;                 // hop
+
+  const int b = blockIdx.y, r = blockIdx.x;
+  const int tbeg = r * n, tend = min(T, tbeg + n);
+  if (tbeg >= tend) return;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) tw_s[i] = a.tw[i];
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = 0.f;
+  __syncthreads();
+  const int half = M / 2 + 1;
+  float* xo = a.xout + (size_t)(b * R + r) * (n + 1) * hop;
+
+  for (int tb = tbeg; tb < tend; tb += G) {
+    const int gv = min(G, tend - tb);
+    float2 *src, *other;
+    if (!a.init) {
+      int first = 0;
+      if (tb != tbeg) {
+        for (int i = threadIdx.x; i < hop; i += blockDim.x) xin_s[i] = xin_s[G * hop + i];
+        first = 1;
+        __syncthreads();
+      }
+      for (int idx = threadIdx.x; idx < (gv + 1 - first) * hop; idx += blockDim.x) {
+        const int c = first + idx / hop, i = idx % hop;
+        xin_s[c * hop + i] = x_padded(a.xin, a.inv_env, b, R, n, hop, T, tb + c, i);
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < G * M; idx += blockDim.x) {
+        const int g = idx / M, m = idx - g * M;
+        float2 z = make_float2(0.f, 0.f);
+        if (g < gv) {
+          const float2 xv = *reinterpret_cast<const float2*>(xin_s + g * hop + 2 * m);
+          const float2 wv = *reinterpret_cast<const float2*>(a.win + 2 * m);
+          z = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
+        bufA[idx] = z;
+      }
+      __syncthreads();
+      float2* res = fft_rows<false>(bufA, bufB, G, M, a.fd, tw_s);
+      for (int idx = threadIdx.x; idx < gv * half; idx += blockDim.x) {
+        const int g = idx / half, k = idx - g * half;
+        const int t = tb + g;
+        const float2 zk = res[g * M + k];
+        const float2 zmk = res[g * M + ((M - k) & -(k != 0))];
+        float2 xk, xmk;
+        rfft_split(zk, zmk, a.rtw[k], xk, xmk);
+        float2* tp = a.tprev + ((size_t)b * T + t) * M;
+        const float* mg = a.mag_tf + ((size_t)b * T + t) * a.Fp;
+        const float mk = mg[k], mmk = mg[M - k];
+        float2 yk, ymk;
+        if (k == 0) {
+          float a0 = xk.x, aM = xmk.x;
+          if (a.use_prev) {
+            const float2 pv = tp[0];
+            a0 -= a.mom * pv.x;
+            aM -= a.mom * pv.y;
+          }
+          yk = make_float2(mk * (a0 / (fabsf(a0) + 1e-16f)), 0.f);
+          ymk = make_float2(mmk * (aM / (fabsf(aM) + 1e-16f)), 0.f);
+          if (a.store_prev) tp[0] = make_float2(xk.x, xmk.x);
+        } else {
+          float2 ak = xk, amk = xmk;
+          if (a.use_prev) {
+            const float2 pk = tp[k], pmk = tp[M - k];
+            ak = make_float2(xk.x - a.mom * pk.x, xk.y - a.mom * pk.y);
+            amk = make_float2(xmk.x - a.mom * pmk.x, xmk.y - a.mom * pmk.y);
+          }
+          const float2 uk = unit_dir(ak), umk = unit_dir(amk);
+          yk = make_float2(mk * uk.x, mk * uk.y);
+          ymk = make_float2(mmk * umk.x, mmk * umk.y);
+          if (a.store_prev) {
+            tp[k] = xk;
+            if (2 * k != M) tp[M - k] = xmk;
+          }
+        }
+        float2 z1, z2;
+        irfft_merge(yk, ymk, a.rtw[k], z1, z2);
+        res[g * M + k] = z1;
+        if (k != 0 && 2 * k != M) res[g * M + M - k] = z2;
+      }
+      __syncthreads();
+      src = res;
+      other = (res == bufA) ? bufB : bufA;
+    } else {
+      for (int idx = threadIdx.x; idx < G * half; idx += blockDim.x) {
+        const int k = idx / G, g = idx - k * G;
+        float2 z1 = make_float2(0.f, 0.f), z2 = z1;
+        if (g < gv) {
+          const int t = tb + g;
+          const float* mg = a.mag_tf + ((size_t)b * T + t) * a.Fp;
+          float2 yk = make_float2(mg[k], 0.f), ymk = make_float2(mg[M - k], 0.f);
+          if (a.angles0) {
+            const float2 ak = a.angles0[((size_t)b * a.F + k) * T + t];
+            const float2 amk = a.angles0[((size_t)b * a.F + (M - k)) * T + t];
+            yk = make_float2(yk.x * ak.x, yk.x * ak.y);
+            ymk = make_float2(ymk.x * amk.x, ymk.x * amk.y);
+          }
+          if (k == 0) { yk.y = 0.f; ymk.y = 0.f; }
+          irfft_merge(yk, ymk, a.rtw[k], z1, z2);
+        }
+        bufA[g * M + k] = z1;
+        if (k != 0 && 2 * k != M) bufA[g * M + M - k] = z2;
+      }
+      __syncthreads();
+      src = bufA;
+      other = bufB;
+    }
+    float2* out = fft_rows<true>(src, other, G, M, a.fd, tw_s);
+    const float* y = reinterpret_cast<const float*>(out);
+    for (int idx = threadIdx.x; idx < gv * hop; idx += blockDim.x) {
+      const int c = idx / hop, i = idx - c * hop;
+      const float prev = (c == 0) ? carry_s[i] : y[(c - 1) * N + hop + i] * a.winn[hop + i];
+      xo[(size_t)(tb - tbeg + c) * hop + i] = prev + y[c * N + i] * a.winn[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = y[(gv - 1) * N + hop + i] * a.winn[hop + i];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) xo[(size_t)(tend - tbeg) * hop + i] = carry_s[i];
+}
+
+// partial hop-block format -> [B, hop*(T-1)] waveform (envelope-normalised, optional per-clip scale)
+__global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict__ part, const float* __restrict__ inv_env,
+                                                        const float* __restrict__ out_scale, float* __restrict__ wave,
+                                                        int T, int n, int R, int hop) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x + 1;  // hop-block 1..T-1
+  const float sc = out_scale ? out_scale[b] : 1.0f;
+  float* dst = wave + (size_t)b * hop * (T - 1) + (size_t)(j - 1) * hop;
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) dst[i] = x_block_sample(part, inv_env, b, R, n, hop, j, i) * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+GlPartition gl_partition(const b2d_plan* p, int B, int T) {
+  GlPartition q;
+  q.G = (p->M <= 1024) ? 4 : 2;
+  q.fast = false;
+  const int target = 4 * p->num_sms;  // CTAs wanted in flight
+  int R = (target + B - 1) / B;
+  const int maxR = (T + q.G - 1) / q.G;
+  if (R > maxR) R = maxR;
+  if (R < 1) R = 1;
+  int n = (T + R - 1) / R;
+  n = (n + q.G - 1) / q.G * q.G;
+  q.n = n;
+  q.R = (T + n - 1) / n;
+  return q;
+}
+
+static size_t part_floats(const b2d_plan* p, const GlPartition& q, int B) {
+  return (size_t)B * q.R * (q.n + 1) * p->hop;
+}
+
+size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
+  const GlPartition q = gl_partition(p, B, T);
+  size_t bytes = 2 * align_up(part_floats(p, q, B) * sizeof(float), 256);
+  bytes += align_up((size_t)B * T * p->M * sizeof(float2), 256);
+  if (need_mag_copy) bytes += align_up((size_t)B * T * p->Fp * sizeof(float), 256);
+  return bytes;
+}
+
+int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, int B, int T, int n_iter, float momentum,
+           const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st) {
+  B2D_REQUIRE(p->hop * 2 == p->n_fft, B2D_ERR_UNSUPPORTED, "Griffin-Lim requires hop == n_fft/2 (got n_fft=%d hop=%d)", p->n_fft, p->hop);
+  B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
+  B2D_REQUIRE(momentum >= 0.f && momentum < 1.f, B2D_ERR_BAD_ARG, "momentum must be in range [0, 1). Found: %g", (double)momentum);
+  B2D_REQUIRE(n_iter >= 0, B2D_ERR_BAD_ARG, "n_iter must be >= 0");
+  B2D_REQUIRE(B >= 1 && B <= 65535, B2D_ERR_BAD_ARG, "batch must be in [1, 65535] per call (got %d)", B);
+  B2D_REQUIRE(ws_bytes >= gl_workspace_bytes(p, B, T, false), B2D_ERR_WORKSPACE, "Griffin-Lim workspace too small");
+  const GlPartition q = gl_partition(p, B, T);
+  const size_t pbytes = align_up(part_floats(p, q, B) * sizeof(float), 256);
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  float* xa = reinterpret_cast<float*>(base);
+  float* xb = reinterpret_cast<float*>(base + pbytes);
+  float2* tprev = reinterpret_cast<float2*>(base + 2 * pbytes);
+
+  GlArgs a;
+  a.mag_tf = mag_tf; a.angles0 = init_angles; a.tprev = tprev;
+  a.B = B; a.T = T; a.n = q.n; a.R = q.R; a.G = q.G;
+  a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.Fp = p->Fp; a.fd = p->fft;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.mom = momentum / (1.0f + momentum);
+  const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * q.G * p->M) + sizeof(float) * (size_t)((q.G + 2) * p->hop) + 16;
+  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(q.R, B);
+  // x_0 = istft(mag * angles_0)
+  a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa;
+  gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+  B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
+  float* cur = xa;
+  float* nxt = xb;
+  a.init = 0; a.angles0 = nullptr;
+  for (int it = 0; it < n_iter; ++it) {
+    a.use_prev = (it > 0 && a.mom != 0.f) ? 1 : 0;
+    a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
+    a.xin = cur; a.xout = nxt;
+    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+    B2D_LAUNCH_CHECK("gl_generic_kernel");
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  gl_stitch_kernel<<<dim3(T - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop);
+  B2D_LAUNCH_CHECK("gl_stitch_kernel");
+  return B2D_OK;
+}
+
+}  // namespace b2d

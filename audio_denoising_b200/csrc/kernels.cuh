@@ -1,0 +1,37 @@
+// kernels.cuh -- internal launcher declarations shared by the translation units of libb200denoise.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2d {
+
+// dsp.cu
+int launch_peak(const float* wave, int B, int L, float* peak, float* partial, int chunks, cudaStream_t st);
+int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
+                float* logmel_bm, float2* spec, cudaStream_t st);
+int launch_mel_scale(const b2d_plan* p, const float* mag, int B, int T, float* mel, cudaStream_t st);
+int launch_residual(const float* x, const float* pred, float* out, size_t n, int mode, float out_scale, cudaStream_t st);
+int launch_inverse_mel(const b2d_plan* p, const float* mel, int B, int T, float* out, bool torch_layout, cudaStream_t st);
+int launch_istft(const b2d_plan* p, const float2* spec, const float* mag, int B, int T, float* wave, cudaStream_t st);
+int launch_to_frame_layout(const float* in, float* out, int B, int F, int T, int Fp, cudaStream_t st);
+
+// griffinlim.cu
+struct GlPartition {
+  int n;  // frames per run
+  int R;  // runs per clip
+  int G;  // frames per round inside a run
+  bool fast;
+};
+GlPartition gl_partition(const b2d_plan* p, int B, int T);
+size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy);
+int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, int B, int T, int n_iter, float momentum,
+           const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// model.cu
+size_t model_workspace_bytes(const b2d_model* m, int B, int T);
+// fused_mode: 0 = write pred only, 1 = also mel (app3 residual), 2 = also mel (server residual, out_scale)
+int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, float* mel_bt, int fused_mode,
+                  float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st);
+int scale_inplace(float* p, size_t n, float s, cudaStream_t st);
+
+}  // namespace b2d

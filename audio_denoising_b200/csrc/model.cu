@@ -1,0 +1,492 @@
+// model.cu -- K3: GRUUNet2 forward (gruunet2.py:54-306), restructured for the GPU:
+//
+//   encoder  (input_gate DownBlocks, gruunet2.py:127-144)  : depends only on x_t  -> all B*T frames in parallel
+//   recurrence (reset_gate conv + gates, gruunet2.py:146-155, 231-240) : the only sequential part; one CTA per
+//              clip, the [51,17,3] recurrent weights live in registers for the whole sequence, gate_x hoisted
+//   decoder  (output_gate UpBlocks, gruunet2.py:184-199)   : depends only on h_t and the skips -> all frames in parallel
+//
+// The GaussianSmearing position channels (gruunet2.py:54-68) are input independent, so their
+// contribution is folded into a per-position bias when the model is packed.
+// This file holds the fp32 CUDA-core convolutions (conv_mode 0, the parity mode); conv_tc.cu holds
+// the tcgen05 implicit-GEMM variants of the encoder / decoder.
+#include <math.h>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace b2d {
+
+// shipped configuration (all three checkpoints): hidden 17, 4 levels, 4 compressed bins
+constexpr int H = 17;
+constexpr int HP = 20;        // hidden padded to a multiple of 4 (float4 weight rows)
+constexpr int H3 = 51;
+constexpr int H3P = 52;
+constexpr int LEVELS = 4;
+constexpr int BINS = 4;
+constexpr int NMEL = BINS << LEVELS;  // 64
+
+// per-frame activation sizes
+constexpr int D0 = H * 32, D1 = H * 16, D2 = H * 8, GX = H3 * 4, HS = H * 4;
+
+// ---- packed parameter blob layout (floats) --------------------------------------------------------
+// encoder layer l : W[ci][k][coP]  ,  PB[j][coP]
+// recurrent       : W[ci][k][gate][c] (c padded to HP) , PB[gate][c][j]
+// decoder layer i : W[ci][k][coP]  ,  PB[o][coP]
+struct Packed {
+  int enc_w[LEVELS], enc_pb[LEVELS];
+  int rec_w, rec_pb;
+  int dec_w[LEVELS], dec_pb[LEVELS];
+  int total;
+};
+__host__ __device__ inline Packed packed_layout() {
+  Packed p{};
+  int o = 0;
+  const int cin[LEVELS] = {1, H, H, H};
+  const int cop[LEVELS] = {HP, HP, HP, H3P};
+  const int lout[LEVELS] = {32, 16, 8, 4};
+  for (int l = 0; l < LEVELS; ++l) {
+    p.enc_w[l] = o; o += cin[l] * 3 * cop[l];
+    p.enc_pb[l] = o; o += lout[l] * cop[l];
+  }
+  p.rec_w = o; o += H * 3 * 3 * HP;
+  p.rec_pb = o; o += 3 * H * 4;
+  const int dcin[LEVELS] = {H, 2 * H, 2 * H, 2 * H};
+  const int dcop[LEVELS] = {HP, HP, HP, 4};
+  const int dlout[LEVELS] = {8, 16, 32, 64};
+  for (int i = 0; i < LEVELS; ++i) {
+    p.dec_w[i] = o; o += dcin[i] * 3 * dcop[i];
+    p.dec_pb[i] = o; o += dlout[i] * dcop[i];
+  }
+  p.total = o;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder: one warp per frame.  Work item = (output position j, group of 4 output channels).
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COP, int LIN>
+__device__ __forceinline__ void enc_layer(const float* __restrict__ in, const float* __restrict__ W,
+                                          const float* __restrict__ PB, float* __restrict__ out, int cout, int lane) {
+  constexpr int LOUT = LIN / 2;
+  constexpr int NG = COP / 4;
+  for (int item = lane; item < LOUT * NG; item += 32) {
+    const int j = item % LOUT, cg = item / LOUT;
+    float4 acc = *reinterpret_cast<const float4*>(PB + j * COP + cg * 4);
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* row = in + ci * LIN;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int p = 2 * j - 1 + k;
+        const float v = (p >= 0 && p < LIN) ? row[p] : 0.f;
+        const float4 w = *reinterpret_cast<const float4*>(W + (ci * 3 + k) * COP + cg * 4);
+        acc.x = fmaf(v, w.x, acc.x);
+        acc.y = fmaf(v, w.y, acc.y);
+        acc.z = fmaf(v, w.z, acc.z);
+        acc.w = fmaf(v, w.w, acc.w);
+      }
+    }
+    const float r[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = cg * 4 + q;
+      if (co < cout) out[co * LOUT + j] = r[q];
+    }
+  }
+}
+
+constexpr int ENC_WARPS = 8;
+constexpr int ENC_ACT = NMEL + D0 + D1 + D2 + GX;  // 1220 floats per warp
+
+__global__ void __launch_bounds__(ENC_WARPS * 32) encoder_kernel(const float* __restrict__ blob, const float* __restrict__ x,
+                                                                 size_t nframes, float* __restrict__ d0, float* __restrict__ d1,
+                                                                 float* __restrict__ d2, float* __restrict__ gx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Packed L = packed_layout();
+  float* wts = reinterpret_cast<float*>(smem_raw);  // encoder part of the blob: [0, rec_w)
+  const int nw = L.rec_w;
+  float* act = wts + ((nw + 3) & ~3);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* a_in = act + warp * ENC_ACT;
+  float* a0 = a_in + NMEL;
+  float* a1 = a0 + D0;
+  float* a2 = a1 + D1;
+  float* a3 = a2 + D2;
+  for (size_t f = (size_t)blockIdx.x * ENC_WARPS + warp; f < nframes; f += (size_t)gridDim.x * ENC_WARPS) {
+    const float* xf = x + f * NMEL;
+    a_in[lane] = xf[lane];
+    a_in[lane + 32] = xf[lane + 32];
+    __syncwarp();
+    enc_layer<1, HP, 64>(a_in, wts + L.enc_w[0], wts + L.enc_pb[0], a0, H, lane);
+    __syncwarp();
+    enc_layer<H, HP, 32>(a0, wts + L.enc_w[1], wts + L.enc_pb[1], a1, H, lane);
+    __syncwarp();
+    enc_layer<H, HP, 16>(a1, wts + L.enc_w[2], wts + L.enc_pb[2], a2, H, lane);
+    __syncwarp();
+    enc_layer<H, H3P, 8>(a2, wts + L.enc_w[3], wts + L.enc_pb[3], a3, H3, lane);
+    __syncwarp();
+    for (int i = lane; i < D0; i += 32) d0[f * D0 + i] = a0[i];
+    for (int i = lane; i < D1; i += 32) d1[f * D1 + i] = a1[i];
+    for (int i = lane; i < D2; i += 32) d2[f * D2 + i] = a2[i];
+    for (int i = lane; i < GX; i += 32) gx[f * GX + i] = a3[i];
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// recurrence: one CTA (96 threads, 68 active) per clip; thread (c, j) owns hidden channel c at
+// compressed bin j and keeps its 3 x 17 x 3 recurrent weights in registers for all T steps.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict__ blob, const float* __restrict__ gx,
+                                                        float* __restrict__ hx, float* __restrict__ hseq, int T) {
+  const Packed L = packed_layout();
+  __shared__ float hp[H][BINS + 2];  // zero padded at both ends
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool active = tid < H * BINS;
+  const int c = active ? tid / BINS : 0, j = active ? tid % BINS : 0;
+  float w[3][H][3];
+  float pb[3];
+  {
+    const float* W = blob + L.rec_w;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int ci = 0; ci < H; ++ci)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[g][ci][k] = W[((ci * 3 + k) * 3 + g) * HP + c];
+      pb[g] = blob[L.rec_pb + (g * H + c) * BINS + j];
+    }
+  }
+  for (int i = tid; i < H * (BINS + 2); i += blockDim.x) (&hp[0][0])[i] = 0.f;
+  __syncthreads();
+  float h = 0.f;
+  if (active) {
+    h = hx[(size_t)b * HS + c * BINS + j];
+    hp[c][j + 1] = h;
+  }
+  __syncthreads();
+  const float* gxb = gx + (size_t)b * T * GX;
+  float* hsb = hseq + (size_t)b * T * HS;
+  float xr = 0.f, xz = 0.f, xn = 0.f;
+  if (active && T > 0) {
+    xr = gxb[c * BINS + j];
+    xz = gxb[(H + c) * BINS + j];
+    xn = gxb[(2 * H + c) * BINS + j];
+  }
+  for (int t = 0; t < T; ++t) {
+    float nr = 0.f, nz = 0.f, nn = 0.f;
+    if (active && t + 1 < T) {  // prefetch next step's hoisted input gates
+      const float* g1 = gxb + (size_t)(t + 1) * GX;
+      nr = g1[c * BINS + j];
+      nz = g1[(H + c) * BINS + j];
+      nn = g1[(2 * H + c) * BINS + j];
+    }
+    float ar = pb[0], az = pb[1], an = pb[2];
+#pragma unroll
+    for (int ci = 0; ci < H; ++ci) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float v = hp[ci][j + k];
+        ar = fmaf(w[0][ci][k], v, ar);
+        az = fmaf(w[1][ci][k], v, az);
+        an = fmaf(w[2][ci][k], v, an);
+      }
+    }
+    ar = fmaxf(ar, 0.f);  // both pre-activations went through ReLU (gruunet2.py:71-79, Q8)
+    az = fmaxf(az, 0.f);
+    an = fmaxf(an, 0.f);
+    const float z = sigmoidf_(xz + az);
+    const float r = sigmoidf_(xr + ar);
+    const float nw = tanhf(xn + r * an);
+    const float hn = nw + z * (h - nw);
+    __syncthreads();  // everyone has read hp for this step
+    if (active) {
+      hp[c][j + 1] = hn;
+      hsb[(size_t)t * HS + c * BINS + j] = hn;
+    }
+    h = hn;
+    xr = nr; xz = nz; xn = nn;
+    __syncthreads();
+  }
+  if (active) hx[(size_t)b * HS + c * BINS + j] = h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder: one warp per frame.  ConvTranspose1d(k3,s2,p1,op1):
+//   out[co,2j]   = pb + sum_ci x[ci,j] W[ci,1,co]
+//   out[co,2j+1] = pb + sum_ci (x[ci,j] W[ci,2,co] + x[ci,j+1] W[ci,0,co])
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COP, int LIN, bool RELU>
+__device__ __forceinline__ void dec_layer(const float* __restrict__ in, const float* __restrict__ W,
+                                          const float* __restrict__ PB, float* __restrict__ out, int cout, int lane) {
+  constexpr int LOUT = LIN * 2;
+  constexpr int NG = COP / 4;
+  for (int item = lane; item < LOUT * NG; item += 32) {
+    const int o = item % LOUT, cg = item / LOUT;
+    const int j = o >> 1;
+    const bool odd = o & 1;
+    float4 acc = *reinterpret_cast<const float4*>(PB + o * COP + cg * 4);
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* row = in + ci * LIN;
+      const float v0 = row[j];
+      const float4 w0 = *reinterpret_cast<const float4*>(W + (ci * 3 + (odd ? 2 : 1)) * COP + cg * 4);
+      acc.x = fmaf(v0, w0.x, acc.x);
+      acc.y = fmaf(v0, w0.y, acc.y);
+      acc.z = fmaf(v0, w0.z, acc.z);
+      acc.w = fmaf(v0, w0.w, acc.w);
+      if (odd && j + 1 < LIN) {
+        const float v1 = row[j + 1];
+        const float4 w1 = *reinterpret_cast<const float4*>(W + (ci * 3 + 0) * COP + cg * 4);
+        acc.x = fmaf(v1, w1.x, acc.x);
+        acc.y = fmaf(v1, w1.y, acc.y);
+        acc.z = fmaf(v1, w1.z, acc.z);
+        acc.w = fmaf(v1, w1.w, acc.w);
+      }
+    }
+    float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = cg * 4 + q;
+      if (co < cout) out[co * LOUT + o] = RELU ? fmaxf(r[q], 0.f) : r[q];
+    }
+  }
+}
+
+constexpr int DEC_WARPS = 8;
+// per-warp activations: u0 [34][4->8]: stage inputs are [2H][L] with rows 0..H-1 = upsampled, H..2H-1 = skip
+constexpr int DEC_ACT = H * 4 + 2 * H * 8 + 2 * H * 16 + 2 * H * 32 + 64;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32) decoder_kernel(const float* __restrict__ blob, const float* __restrict__ hseq,
+                                                                 const float* __restrict__ d0, const float* __restrict__ d1,
+                                                                 const float* __restrict__ d2, const float* __restrict__ x,
+                                                                 size_t nframes, float* __restrict__ pred,
+                                                                 float* __restrict__ mel, int fused_mode, float out_scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Packed L = packed_layout();
+  float* wts = reinterpret_cast<float*>(smem_raw);
+  const int w0 = L.dec_w[0];
+  const int nw = L.total - w0;
+  float* act = wts + ((nw + 3) & ~3);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[w0 + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s0 = act + warp * DEC_ACT;  // [H][4]
+  float* s1 = s0 + H * 4;            // [2H][8]
+  float* s2 = s1 + 2 * H * 8;        // [2H][16]
+  float* s3 = s2 + 2 * H * 16;       // [2H][32]
+  float* s4 = s3 + 2 * H * 32;       // [1][64]
+  for (size_t f = (size_t)blockIdx.x * DEC_WARPS + warp; f < nframes; f += (size_t)gridDim.x * DEC_WARPS) {
+    for (int i = lane; i < HS; i += 32) s0[i] = hseq[f * HS + i];
+    for (int i = lane; i < D2; i += 32) s1[H * 8 + i] = d2[f * D2 + i];
+    for (int i = lane; i < D1; i += 32) s2[H * 16 + i] = d1[f * D1 + i];
+    for (int i = lane; i < D0; i += 32) s3[H * 32 + i] = d0[f * D0 + i];
+    __syncwarp();
+    dec_layer<H, HP, 4, true>(s0, wts + (L.dec_w[0] - w0), wts + (L.dec_pb[0] - w0), s1, H, lane);
+    __syncwarp();
+    dec_layer<2 * H, HP, 8, true>(s1, wts + (L.dec_w[1] - w0), wts + (L.dec_pb[1] - w0), s2, H, lane);
+    __syncwarp();
+    dec_layer<2 * H, HP, 16, true>(s2, wts + (L.dec_w[2] - w0), wts + (L.dec_pb[2] - w0), s3, H, lane);
+    __syncwarp();
+    dec_layer<2 * H, 4, 32, false>(s3, wts + (L.dec_w[3] - w0), wts + (L.dec_pb[3] - w0), s4, 1, lane);
+    __syncwarp();
+    for (int i = lane; i < NMEL; i += 32) {
+      const float p = s4[i];
+      pred[f * NMEL + i] = p;
+      if (fused_mode) {
+        const float xv = x[f * NMEL + i];
+        float v;
+        if (fused_mode == 1) {
+          float r = xv - p;
+          r = r > 0.f ? r : 0.2f * r;
+          v = fmaxf(expm1f(r), 0.f);
+        } else {
+          v = expf(xv - fmaxf(p, 0.f) * out_scale) - 1.0f;
+        }
+        mel[f * NMEL + i] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void scale_kernel(float* p, size_t n, float s) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] *= s;
+}
+int scale_inplace(float* p, size_t n, float s, cudaStream_t st) {
+  if (n == 0) return B2D_OK;
+  scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, s);
+  B2D_LAUNCH_CHECK("scale_kernel");
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: packing
+// ------------------------------------------------------------------------------------------------
+static void smear_table(const float* off, int G, int nbins, std::vector<double>& s) {
+  // gruunet2.py:54-68: exp(coeff * (p - o)^2), p = linspace(0,1,nbins), coeff = -0.5/(o[1]-o[0])^2 (f32 gap)
+  const double gap = (double)(float)(off[1] - off[0]);
+  const double coeff = -0.5 / (gap * gap);
+  s.assign((size_t)G * nbins, 0.0);
+  for (int p = 0; p < nbins; ++p) {
+    const double pos = (nbins > 1) ? (double)(float)((double)p / (double)(nbins - 1)) : 0.0;
+    for (int g = 0; g < G; ++g) {
+      const double d = (double)(float)(pos - (double)off[g]);
+      s[(size_t)g * nbins + p] = exp((double)(float)coeff * (double)(float)(d * d));
+    }
+  }
+}
+
+int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
+  const Packed L = packed_layout();
+  const int G = m->cfg.num_gaussians;
+  std::vector<float> blob((size_t)L.total, 0.f);
+  std::vector<double> S;
+  // encoder: params 2l (weight [co][ci+G][3]) , 2l+1 (bias [co])
+  const int cin[LEVELS] = {1, H, H, H};
+  const int cout[LEVELS] = {H, H, H, H3};
+  const int cop[LEVELS] = {HP, HP, HP, H3P};
+  const int lin[LEVELS] = {64, 32, 16, 8};
+  for (int l = 0; l < LEVELS; ++l) {
+    const float* W = hp[2 * l];
+    const float* bias = hp[2 * l + 1];
+    const int CT = cin[l] + G, Lin = lin[l], Lout = Lin / 2;
+    smear_table(offs[0], G, Lin, S);
+    for (int co = 0; co < cout[l]; ++co) {
+      for (int ci = 0; ci < cin[l]; ++ci)
+        for (int k = 0; k < 3; ++k) blob[L.enc_w[l] + (ci * 3 + k) * cop[l] + co] = W[(co * CT + ci) * 3 + k];
+      for (int j = 0; j < Lout; ++j) {
+        double acc = bias[co];
+        for (int g = 0; g < G; ++g)
+          for (int k = 0; k < 3; ++k) {
+            const int p = 2 * j - 1 + k;
+            if (p >= 0 && p < Lin) acc += (double)W[(co * CT + cin[l] + g) * 3 + k] * S[(size_t)g * Lin + p];
+          }
+        blob[L.enc_pb[l] + j * cop[l] + co] = (float)acc;
+      }
+    }
+  }
+  // recurrent conv: params 2*LEVELS, 2*LEVELS+1 ; weight [3H][H+G][3], stride 1, pad 1, length BINS
+  {
+    const float* W = hp[2 * LEVELS];
+    const float* bias = hp[2 * LEVELS + 1];
+    const int CT = H + G;
+    smear_table(offs[1], G, BINS, S);
+    for (int g3 = 0; g3 < 3; ++g3)
+      for (int c = 0; c < H; ++c) {
+        const int co = g3 * H + c;
+        for (int ci = 0; ci < H; ++ci)
+          for (int k = 0; k < 3; ++k) blob[L.rec_w + ((ci * 3 + k) * 3 + g3) * HP + c] = W[(co * CT + ci) * 3 + k];
+        for (int j = 0; j < BINS; ++j) {
+          double acc = bias[co];
+          for (int g = 0; g < G; ++g)
+            for (int k = 0; k < 3; ++k) {
+              const int p = j - 1 + k;
+              if (p >= 0 && p < BINS) acc += (double)W[(co * CT + H + g) * 3 + k] * S[(size_t)g * BINS + p];
+            }
+          blob[L.rec_pb + co * BINS + j] = (float)acc;
+        }
+      }
+  }
+  // decoder: params 2*LEVELS+2+2i ; ConvTranspose weight [ci+G][co][3]
+  const int dcin[LEVELS] = {H, 2 * H, 2 * H, 2 * H};
+  const int dcout[LEVELS] = {H, H, H, 1};
+  const int dcop[LEVELS] = {HP, HP, HP, 4};
+  const int dlin[LEVELS] = {4, 8, 16, 32};
+  for (int i = 0; i < LEVELS; ++i) {
+    const float* W = hp[2 * LEVELS + 2 + 2 * i];
+    const float* bias = hp[2 * LEVELS + 3 + 2 * i];
+    const int Lin = dlin[i], CO = dcout[i];
+    smear_table(offs[2], G, Lin, S);
+    for (int co = 0; co < CO; ++co) {
+      for (int ci = 0; ci < dcin[i]; ++ci)
+        for (int k = 0; k < 3; ++k) blob[L.dec_w[i] + (ci * 3 + k) * dcop[i] + co] = W[(ci * CO + co) * 3 + k];
+      for (int o = 0; o < 2 * Lin; ++o) {
+        const int j = o >> 1;
+        double acc = bias[co];
+        for (int g = 0; g < G; ++g) {
+          const float* Wg = W + ((dcin[i] + g) * CO + co) * 3;
+          if (o & 1) {
+            acc += (double)Wg[2] * S[(size_t)g * Lin + j];
+            if (j + 1 < Lin) acc += (double)Wg[0] * S[(size_t)g * Lin + j + 1];
+          } else {
+            acc += (double)Wg[1] * S[(size_t)g * Lin + j];
+          }
+        }
+        blob[L.dec_pb[i] + o * dcop[i] + co] = (float)acc;
+      }
+    }
+  }
+  m->blob_floats = blob.size();
+  B2D_CUDA(cudaMalloc(&m->d_blob, blob.size() * sizeof(float)));
+  B2D_CUDA(cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return B2D_OK;
+}
+
+bool model_config_supported(const b2d_model_config* c) {
+  return c->hidden == H && c->levels == LEVELS && c->num_compressed_bins == BINS && c->kernel == 3 && c->stride == 2 &&
+         c->padding == 1 && c->num_gaussians >= 2 && c->num_gaussians <= 16;
+}
+
+// workspace: d0 | d1 | d2 | gx | hseq   (per frame: D0+D1+D2+GX+HS floats)
+size_t model_workspace_bytes(const b2d_model* m, int B, int T) {
+  (void)m;
+  const size_t nf = (size_t)B * T;
+  return align_up(nf * D0 * 4, 256) + align_up(nf * D1 * 4, 256) + align_up(nf * D2 * 4, 256) + align_up(nf * GX * 4, 256) +
+         align_up(nf * HS * 4, 256);
+}
+
+int model_forward_tc(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx,
+                     int conv_mode, cudaStream_t st);  // conv_tc.cu
+int model_decode_tc(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
+                    size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int conv_mode, cudaStream_t st);
+
+int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, float* mel_bt, int fused_mode,
+                  float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "GRUUNet2 forward needs B >= 1 and T >= 1 (got %d, %d)", B, T);
+  B2D_REQUIRE(ws != nullptr && ws_bytes >= model_workspace_bytes(m, B, T), B2D_ERR_WORKSPACE, "GRUUNet2 workspace too small");
+  B2D_REQUIRE(conv_mode >= 0 && conv_mode <= 2, B2D_ERR_BAD_ARG, "conv_mode must be 0, 1 or 2");
+  const size_t nf = (size_t)B * T;
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  float* d0 = reinterpret_cast<float*>(base); base += align_up(nf * D0 * 4, 256);
+  float* d1 = reinterpret_cast<float*>(base); base += align_up(nf * D1 * 4, 256);
+  float* d2 = reinterpret_cast<float*>(base); base += align_up(nf * D2 * 4, 256);
+  float* gx = reinterpret_cast<float*>(base); base += align_up(nf * GX * 4, 256);
+  float* hseq = reinterpret_cast<float*>(base);
+  const Packed L = packed_layout();
+  int dev_sms = 148;
+  if (conv_mode == 0) {
+    const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
+    B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
+    const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
+    encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
+    B2D_LAUNCH_CHECK("encoder_kernel");
+  } else {
+    int rc = model_forward_tc(m, x, nf, d0, d1, d2, gx, conv_mode, st);
+    if (rc != B2D_OK) return rc;
+  }
+  recurrence_kernel<<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
+  B2D_LAUNCH_CHECK("recurrence_kernel");
+  if (conv_mode == 0) {
+    const int nw = L.total - L.dec_w[0];
+    const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC_WARPS * DEC_ACT);
+    B2D_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t want = (nf + DEC_WARPS - 1) / DEC_WARPS;
+    const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
+    decoder_kernel<<<grid, DEC_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
+    B2D_LAUNCH_CHECK("decoder_kernel");
+  } else {
+    int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, st);
+    if (rc != B2D_OK) return rc;
+  }
+  return B2D_OK;
+}
+
+}  // namespace b2d

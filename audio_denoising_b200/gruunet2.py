@@ -1,0 +1,168 @@
+"""Drop-in ``GRUUNet2`` (reference: gruunet2.py:246-306) running on the sm_100a kernels.
+
+Same constructor, same ``state_dict`` keys / ``parameters()`` order, same
+``forward(input, hx=None) -> (out, hx)`` with the 2-D / 3-D input handling of gruunet2.py:290-306,
+same ``.hparams`` / ``.get_config()`` / ``.from_config`` helpers (gruunet2.py:29-51) -- so
+``load_state_dict`` of the shipped checkpoints and ``TrainingContext.load`` (server.py:129-142)
+work unchanged.  The parameter holders are real ``nn.Conv1d`` / ``nn.ConvTranspose1d`` modules so
+that seeded construction draws the same initial weights as the reference, but they are never
+*called*: ``forward`` packs the weights into a native model (Gaussian position channels folded into
+per-position biases) and runs encoder -> persistent recurrence -> decoder kernels.
+
+Inference only (the reference calls the model under ``torch.no_grad()``, app3.py:200, server.py:211);
+CUDA float32 tensors only; no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _cabi
+from ._runtime import Workspace, require_cuda_f32, stream_ptr
+
+CONV_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+class _PositionCode(nn.Module):
+    """Holder of the ``gs.offset`` buffer (GaussianSmearing centres, gruunet2.py:54-68)."""
+
+    def __init__(self, count: int):
+        super().__init__()
+        self.register_buffer("offset", torch.linspace(0.0, 1.0, count))
+
+
+class _Slot(nn.Module):
+    """One ``...{i}.conv`` parameter holder."""
+
+    def __init__(self, conv: nn.Module):
+        super().__init__()
+        self.conv = conv
+
+
+class _Encoder(nn.Module):  # state_dict prefix "downs.{i}.conv", "gs.offset"
+    def __init__(self, channels: Sequence[int], kernels, strides, paddings, count: int):
+        super().__init__()
+        self.downs = nn.ModuleList()
+        self.gs = _PositionCode(count)
+        for i in range(len(channels) - 1):
+            self.downs.append(_Slot(nn.Conv1d(channels[i] + count, channels[i + 1], kernel_size=kernels[i], stride=strides[i], padding=paddings[i])))
+
+
+class _Decoder(nn.Module):  # state_dict prefix "ups.{i}.conv", "gs.offset"
+    def __init__(self, channels: Sequence[int], kernels, strides, paddings, count: int):
+        super().__init__()
+        self.ups = nn.ModuleList()
+        n = len(channels) - 1
+        for i in range(n):
+            cin = channels[i] + count if i == 0 else 2 * channels[i] + count
+            self.ups.append(_Slot(nn.ConvTranspose1d(cin, channels[i + 1], kernel_size=kernels[i], padding=paddings[i], stride=strides[i])))
+        self.gs = _PositionCode(count)
+
+
+class _Cell(nn.Module):  # "input_gate", "reset_gate", "output_gate"
+    def __init__(self, in_size, hidden_sizes, kernel_sizes, strides, paddings, count):
+        super().__init__()
+        hs = list(hidden_sizes)
+        wide = hs[:-1] + [3 * hs[-1]]
+        self.input_gate = _Encoder([in_size] + wide, list(kernel_sizes), list(strides), list(paddings), count)
+        self.reset_gate = _Encoder([hs[-1], 3 * hs[-1]], [3], [1], [1], count)
+        self.output_gate = _Decoder(hs[::-1] + [1], list(kernel_sizes)[::-1], list(strides)[::-1], list(paddings)[::-1], count)
+
+
+class GRUUNet2(nn.Module):
+    def __init__(self, num_compressed_bins, in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians=6):
+        super().__init__()
+        assert in_size == 1
+        self.hparams = dict(
+            num_compressed_bins=num_compressed_bins, in_size=in_size, hidden_sizes=hidden_sizes, kernel_sizes=kernel_sizes,
+            strides=strides, paddings=paddings, num_gaussians=num_gaussians,
+        )
+        self.latent_size = hidden_sizes[-1]
+        self.num_compressed_bins = num_compressed_bins
+        self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
+        self.conv_mode = "fp32"  # "fp32" (CUDA cores, parity) | "bf16x3" | "bf16" (tcgen05 implicit GEMM)
+        self._native = None  # (signature, handle, finalizer)
+        self._ws = Workspace()
+
+    # ---- gruunet2.py:29-51 helpers ------------------------------------------------------------
+    def get_config(self):
+        return self.hparams
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(**config)
+
+    @property
+    def n_mels(self) -> int:
+        return self.num_compressed_bins << len(self.hparams["hidden_sizes"])
+
+    # ---- native model management -------------------------------------------------------------
+    def _signature(self):
+        ps = list(self.parameters()) + list(self.buffers())
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+
+    def native_handle(self, device: torch.device):
+        """Pack (or re-pack after any weight change) the parameters into a native b2d_model."""
+        sig = (self._signature(), device.index)
+        if self._native is not None and self._native[0] == sig:
+            return self._native[1]
+        hp = self.hparams
+        hs = list(hp["hidden_sizes"])
+        uniform = all(h == hs[0] for h in hs)
+        ks, ss, pp = set(hp["kernel_sizes"]), set(hp["strides"]), set(hp["paddings"])
+        if not (uniform and len(ks) == 1 and len(ss) == 1 and len(pp) == 1):
+            raise NotImplementedError(f"GRUUNet2 (B200): non-uniform layer config is not implemented: {hp}")
+        cfg = _cabi.ModelConfig(hp["num_compressed_bins"], hs[0], len(hs), ks.pop(), ss.pop(), pp.pop(), hp["num_gaussians"])
+        params = [p.detach().to("cpu", torch.float32).contiguous() for p in self.parameters()]
+        offs = [g.gs.offset.detach().to("cpu", torch.float32).contiguous()
+                for g in (self.cell.input_gate, self.cell.reset_gate, self.cell.output_gate)]
+        parr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        oarr = (C.c_void_p * 3)(*[o.data_ptr() for o in offs])
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.lib().b2d_model_create(C.byref(cfg), parr, len(params), oarr, C.byref(handle)))
+        if self._native is not None:
+            self._native[2]()  # destroy the stale native model now
+        fin = weakref.finalize(self, _cabi.lib().b2d_model_destroy, handle)
+        self._native = (sig, handle, fin)
+        return handle
+
+    def _apply(self, fn, *a, **k):  # .to()/.cuda() move the holders; the native pack follows lazily
+        return super()._apply(fn, *a, **k)
+
+    # ---- forward (gruunet2.py:290-306) -------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input: torch.Tensor, hx: Optional[torch.Tensor] = None):
+        two_dimmed = input.dim() == 2
+        if two_dimmed:
+            input = input.unsqueeze(0)
+        if input.dim() != 3:
+            raise Exception(f"unknown!! {input.shape}")
+        x = require_cuda_f32(input, "input")
+        B, T, nm = x.shape
+        if nm != self.n_mels:
+            raise ValueError(f"GRUUNet2 expects {self.n_mels} mel bins on the last axis, got {nm}")
+        if hx is None:
+            h = torch.zeros(B, self.latent_size, self.num_compressed_bins, dtype=x.dtype, device=x.device)
+        else:
+            h = require_cuda_f32(hx, "hx").clone()  # the reference never mutates the caller's hx
+            if tuple(h.shape) != (B, self.latent_size, self.num_compressed_bins):
+                raise ValueError(f"hx must be [{B}, {self.latent_size}, {self.num_compressed_bins}], got {tuple(h.shape)}")
+        out = torch.empty_like(x)
+        if T == 0:
+            return (out.squeeze(0) if two_dimmed else out), h
+        if self.conv_mode not in CONV_MODES:
+            raise ValueError(f"conv_mode must be one of {list(CONV_MODES)}, got {self.conv_mode!r}")
+        lib = _cabi.lib()
+        handle = self.native_handle(x.device)
+        ws = self._ws.get(lib.b2d_gruunet2_workspace_bytes(handle, B, T), x.device)
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.b2d_gruunet2_forward(handle, x.data_ptr(), h.data_ptr(), out.data_ptr(), B, T,
+                                                 CONV_MODES[self.conv_mode], ws.data_ptr(), ws.numel(), stream_ptr(x.device)))
+        if two_dimmed:
+            out = out.squeeze(0)
+        return out, h

@@ -1,0 +1,233 @@
+"""Whole-chain entry points: the inline glue of app3.py:123-250 and server.py:166-220 as objects.
+
+* ``DenoisePipeline.denoise``            -- app3.py:181-217 applied to whole clips [B, L]
+* ``DenoisePipeline.denoise_noisy_phase``-- server.py:207-216 (noisy-phase iSTFT, ``hx *= 0.9`` leak)
+* ``DenoisePipeline.denoise_host``       -- same as ``denoise`` from / to pinned host memory, copies overlapped
+* ``StreamingDenoiser``                  -- ``DenoisingAudioProcessor`` hop loop (app3.py:167-226) with device-resident state
+
+Each call is ONE native call (``b2d_denoise_batch`` / ``b2d_denoise_noisy_phase`` / ``b2d_stream_step``)
+that enqueues the kernel chain on the current CUDA stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._runtime import Workspace, get_plan, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
+from .gruunet2 import CONV_MODES, GRUUNet2
+
+
+class DenoisePipeline:
+    def __init__(self, model: GRUUNet2, n_fft: int = 1024, hop_length: int = 512, n_mels: int = 64, sample_rate: int = 16000,
+                 n_iter: int = 32, momentum: float = 0.99, device: Optional[torch.device] = None):
+        if not isinstance(model, GRUUNet2):
+            raise TypeError("model must be an audio_denoising_b200.GRUUNet2")
+        if n_mels != model.n_mels:
+            raise ValueError(f"n_mels={n_mels} does not match the model ({model.n_mels})")
+        if hop_length * 2 != n_fft:
+            raise NotImplementedError("DenoisePipeline: only hop_length == n_fft // 2 is implemented (the reference's setting)")
+        self.model = model
+        self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop_length, n_mels, sample_rate
+        self.n_iter, self.momentum = n_iter, momentum
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device)
+        if self.plan.rank < n_mels:
+            raise ValueError(f"mel filterbank is rank deficient ({self.plan.rank} < {n_mels}) for n_fft={n_fft}, sample_rate={sample_rate}")
+        self._ws = Workspace()
+        self._host = None
+
+    # -- shapes ---------------------------------------------------------------------------------
+    def num_frames(self, L: int) -> int:
+        return self.plan.num_frames(L)
+
+    def out_length(self, L: int) -> int:
+        return self.plan.out_length(self.plan.num_frames(L))
+
+    def _hx(self, hx, B, device):
+        if hx is None:
+            return torch.zeros(B, self.model.latent_size, self.model.num_compressed_bins, dtype=torch.float32, device=device)
+        return require_cuda_f32(hx, "hx").clone()
+
+    # -- app3 chain -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise(self, noisy: torch.Tensor, hx: Optional[torch.Tensor] = None, init_angles: Optional[torch.Tensor] = None,
+                normalise: bool = True, rand_init: bool = True, return_intermediates: bool = False, out: Optional[torch.Tensor] = None):
+        """noisy [B, L] (CUDA float32) -> wave [B, hop*(T-1)] ; returns (wave, hx) or a dict."""
+        x = require_cuda_f32(noisy, "noisy")
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        B, L = x.shape
+        T = self.plan.num_frames(L)
+        F = self.plan.n_freqs
+        dev = x.device
+        h = self._hx(hx, B, dev)
+        if init_angles is None and rand_init:
+            init_angles = torch.rand((B, F, T), dtype=torch.complex64, device=dev)  # TA functional.py:310
+        if init_angles is not None:
+            init_angles = require_cuda_c64(init_angles, "init_angles").reshape(B, F, T)
+        wave = out if out is not None else torch.empty((B, self.plan.out_length(T)), dtype=torch.float32, device=dev)
+        logmel = pred = mag = None
+        if return_intermediates:
+            logmel = torch.empty((B, T, self.n_mels), dtype=torch.float32, device=dev)
+            pred = torch.empty_like(logmel)
+            mag = torch.empty((B, T, self.plan.frame_stride), dtype=torch.float32, device=dev)
+        lib = _cabi.lib()
+        handle = self.model.native_handle(dev)
+        ws = self._ws.get(lib.b2d_denoise_workspace_bytes(self.plan.handle, handle, B, L), dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.b2d_denoise_batch(
+                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), self.n_iter, float(self.momentum),
+                1 if normalise else 0, CONV_MODES[self.model.conv_mode], wave.data_ptr(), ptr(logmel), ptr(pred), ptr(mag),
+                ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        if return_intermediates:
+            return dict(wave=wave, hx=h, logmel=logmel.transpose(-1, -2), pred=pred, lin_mag=mag[..., :F].transpose(-1, -2))
+        return wave, h
+
+    # -- server chain -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise_noisy_phase(self, x: torch.Tensor, hx: Optional[torch.Tensor] = None, out_scale: float = 3.0, hx_decay: float = 0.9):
+        """server.py:207-216: x [B, L] -> (wave [B, hop*(T-1)], hx) using the noisy phase."""
+        x = require_cuda_f32(x, "x")
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        B, L = x.shape
+        T = self.plan.num_frames(L)
+        dev = x.device
+        h = self._hx(hx, B, dev)
+        wave = torch.empty((B, self.plan.out_length(T)), dtype=torch.float32, device=dev)
+        lib = _cabi.lib()
+        handle = self.model.native_handle(dev)
+        ws = self._ws.get(lib.b2d_denoise_noisy_phase_workspace_bytes(self.plan.handle, handle, B, L), dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.b2d_denoise_noisy_phase(
+                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), float(out_scale), float(hx_decay),
+                CONV_MODES[self.model.conv_mode], wave.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        return wave, h
+
+    # -- host-to-host (end-to-end) ----------------------------------------------------------------
+    @torch.no_grad()
+    def denoise_host(self, noisy_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunks: int = 4,
+                     rand_init: bool = True, init_angles: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """noisy_host [B, L] pinned CPU float32 -> pinned CPU [B, hop*(T-1)].
+
+        The batch is cut into ``chunks`` slices; slice i+1's host->device copy and slice i-1's
+        device->host copy overlap slice i's kernels (three streams, events for ordering).
+        """
+        if noisy_host.is_cuda:
+            raise ValueError("denoise_host takes host tensors; use denoise() for device tensors")
+        B, L = noisy_host.shape
+        T = self.plan.num_frames(L)
+        Lout = self.plan.out_length(T)
+        if out_host is None:
+            out_host = torch.empty((B, Lout), dtype=torch.float32, pin_memory=True)
+        dev = self.device
+        chunks = max(1, min(chunks, B))
+        bounds = [(i * B) // chunks for i in range(chunks + 1)]
+        if self._host is None:
+            self._host = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev))
+        h2d, d2h = self._host["h2d"], self._host["d2h"]
+        compute = torch.cuda.current_stream(dev)
+        h2d.wait_stream(compute)
+        d2h.wait_stream(compute)
+        keep = []
+        for i in range(chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(h2d):
+                xin = noisy_host[lo:hi].to(dev, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(h2d)
+            compute.wait_event(ev_in)
+            ia = None if init_angles is None else init_angles[lo:hi]
+            wave, _ = self.denoise(xin, init_angles=ia, rand_init=rand_init)
+            xin.record_stream(compute)
+            ev_done = torch.cuda.Event()
+            ev_done.record(compute)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(ev_done)
+                out_host[lo:hi].copy_(wave, non_blocking=True)
+                wave.record_stream(d2h)
+            keep.append((xin, wave))
+        compute.wait_stream(d2h)
+        return out_host
+
+
+class StreamingDenoiser:
+    """Device-resident equivalent of ``DenoisingAudioProcessor`` (app3.py:123-250) for S parallel sessions.
+
+    ``push(chunk)`` mirrors ``recv``: it appends samples to the input ring and, for every full ``n_fft`` window,
+    runs one hop (peak normalise, Hann pre-window, 3-frame STFT -> Mel -> GRUUNet2 (hx carried) -> inverse Mel ->
+    Griffin-Lim -> x peak -> overlap-add ring) and returns the ``hop`` samples emitted, one hop late, exactly as
+    app3.py:219-226 does (quirks Q2-Q4 kept).  ``angles_fn(hop_index, shape)`` may supply the Griffin-Lim init.
+    """
+
+    def __init__(self, model: GRUUNet2, n_fft: int = 1536, hop_length: int = 768, n_mels: int = 64, sample_rate: int = 48000,
+                 n_iter: int = 32, momentum: float = 0.99, sessions: int = 1, device: Optional[torch.device] = None, angles_fn=None):
+        if hop_length * 2 != n_fft:
+            raise NotImplementedError("StreamingDenoiser: only hop_length == n_fft // 2 is implemented")
+        self.model = model
+        self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop_length, n_mels, sample_rate
+        self.n_iter, self.momentum, self.S = n_iter, momentum, sessions
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device)
+        if self.plan.rank < n_mels:
+            raise ValueError(f"mel filterbank is rank deficient ({self.plan.rank} < {n_mels}) for n_fft={n_fft}, sample_rate={sample_rate}")
+        self.angles_fn = angles_fn
+        self.hx = torch.zeros(sessions, model.latent_size, model.num_compressed_bins, dtype=torch.float32, device=self.device)
+        self.ola = torch.zeros(sessions, n_fft, dtype=torch.float32, device=self.device)
+        self.inbuf = np.zeros((sessions, 0), dtype=np.float32)
+        self.hops = 0
+        self._ws = Workspace()
+        self._chunk_host = torch.empty((sessions, n_fft), dtype=torch.float32, pin_memory=True)
+        self._out_host = torch.empty((sessions, hop_length), dtype=torch.float32, pin_memory=True)
+        self._chunk_dev = torch.empty((sessions, n_fft), dtype=torch.float32, device=self.device)
+        self._out_dev = torch.empty((sessions, hop_length), dtype=torch.float32, device=self.device)
+
+    @torch.no_grad()
+    def step(self, window: np.ndarray) -> np.ndarray:
+        """One hop: window [S, n_fft] float32 host -> [S, hop] float32 host (includes H2D and D2H, like app3.py:189,215)."""
+        dev = self.device
+        self._chunk_host.numpy()[...] = window
+        self._chunk_dev.copy_(self._chunk_host, non_blocking=True)
+        F = self.plan.n_freqs
+        init = None
+        if self.angles_fn is not None:
+            init = self.angles_fn(self.hops, (self.S, F, 3))
+        elif self.n_iter >= 0:
+            init = torch.rand((self.S, F, 3), dtype=torch.complex64, device=dev)
+        if init is not None:
+            init = require_cuda_c64(init.to(dev), "init_angles")
+        lib = _cabi.lib()
+        handle = self.model.native_handle(dev)
+        ws = self._ws.get(lib.b2d_stream_step_workspace_bytes(self.plan.handle, handle, self.S), dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.b2d_stream_step(
+                self.plan.handle, handle, self._chunk_dev.data_ptr(), self.S, self.hx.data_ptr(), self.ola.data_ptr(), ptr(init),
+                self.n_iter, float(self.momentum), CONV_MODES[self.model.conv_mode], self._out_dev.data_ptr(),
+                ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        self._out_host.copy_(self._out_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        self.hops += 1
+        return self._out_host.numpy().copy()
+
+    def push(self, chunk: np.ndarray) -> np.ndarray:
+        """chunk: [n] or [S, n] float32 samples (or int16, scaled by 1/32767 as app3.py:172).  Returns [S, k*hop]."""
+        c = np.asarray(chunk)
+        if c.dtype == np.int16:
+            c = c.astype(np.float32) / np.iinfo(np.int16).max
+        c = c.astype(np.float32).reshape(self.S, -1) if c.ndim > 1 else np.broadcast_to(c.astype(np.float32), (self.S, c.shape[0]))
+        self.inbuf = np.concatenate([self.inbuf, c], axis=1)
+        outs = []
+        while self.inbuf.shape[1] >= self.n_fft:
+            outs.append(self.step(self.inbuf[:, : self.n_fft]))
+            self.inbuf = self.inbuf[:, self.hop:]
+        if not outs:
+            return np.zeros((self.S, 0), dtype=np.float32)
+        return np.concatenate(outs, axis=1)
+
+    @staticmethod
+    def to_int16(x: np.ndarray) -> np.ndarray:
+        """app3.py:244-245."""
+        return (np.clip(x, -1.0, 1.0) * np.iinfo(np.int16).max).astype(np.int16)

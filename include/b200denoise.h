@@ -1,0 +1,178 @@
+/*
+ * b200denoise.h -- C-ABI of libb200denoise.so: the B200 (sm_100a) implementation of the
+ * belacks/audio-denoising inference hot path
+ *
+ *   waveform -> STFT -> Mel log-magnitude -> GRUUNet2 -> inverse Mel -> Griffin-Lim -> iSTFT/OLA
+ *
+ * The reference is pure Python: it has no FFI.  Each entry point below replaces one *library
+ * call site* of the reference (torchaudio / torch ops, or the reference's own nn.Module), cited
+ * as file:line into the reference tree (`TA:` = torchaudio site-packages).  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer argument is a raw pointer; `const float* wave` etc. are DEVICE pointers unless
+ *     the name starts with `h_` (host);  sizes are plain ints;  `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream).
+ *   - return value: 0 = B2D_OK, <0 = error; b2d_last_error_string() describes the last error of
+ *     the calling thread.  Nothing throws, nothing synchronises the stream, nothing allocates
+ *     device memory after plan/model creation: scratch space is a caller-owned workspace sized by
+ *     the matching *_workspace_bytes() call.
+ *   - plans and models are immutable after creation and may be shared by threads/streams;
+ *     per-stream mutable state (hx, Griffin-Lim iterates, streaming rings) lives in caller buffers.
+ *   - layouts: "torch layout" spectrogram = [B, F, T] (time contiguous, F = n_fft/2+1,
+ *     T = 1 + L/hop); "frame layout" = [B, T, Fp] with Fp = n_fft/2 + 4 (frequency contiguous,
+ *     16-byte aligned rows) is what the fused chain uses internally.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef B200DENOISE_H_
+#define B200DENOISE_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_OK 0
+#define B2D_ERR_BAD_ARG (-1)     /* NULL pointer, non-positive size, inconsistent shapes        */
+#define B2D_ERR_UNSUPPORTED (-2) /* geometry / model config outside what the kernels implement  */
+#define B2D_ERR_ALIGN (-3)       /* pointer not aligned as required (16 B for wave/spec rows)   */
+#define B2D_ERR_CUDA (-4)        /* a CUDA runtime call or launch failed                        */
+#define B2D_ERR_WORKSPACE (-5)   /* workspace NULL or smaller than *_workspace_bytes()          */
+
+typedef struct b2d_plan b2d_plan;   /* DSP geometry + constant tables (twiddles, window, mel, pinv) */
+typedef struct b2d_model b2d_model; /* packed GRUUNet2 weights                                      */
+
+/* Complex numbers are interleaved (re, im) float pairs == torch.complex64 == float2. */
+typedef struct { float re, im; } b2d_c64;
+
+int b2d_version(void);
+const char* b2d_last_error_string(void);
+
+/* ---- plan -------------------------------------------------------------------------------------
+ * Geometry of Spectrogram/MelScale/InverseMelScale/GriffinLim as constructed at app3.py:135-153 and
+ * server.py:173-176: win_length == n_fft, periodic Hann, center=True, reflect padding, onesided.
+ * h_mel_fb: host [F, n_mels] row-major triangular filterbank (TA:functional/functional.py:518-588),
+ * h_pinv  : host [F, n_mels] row-major pinv(fb^T) (min-norm lstsq of TA:transforms/_transforms.py:508).
+ * The STFT supports any 1 <= hop <= n_fft; iSTFT / Griffin-Lim require hop == n_fft/2 (the only
+ * setting the reference uses: app3.py:29-33, server.py:166-170).
+ * n_fft must be even with n_fft/2 = 2^a 3^b 5^c and 64 <= n_fft <= 4096. */
+int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, b2d_plan** out);
+void b2d_plan_destroy(b2d_plan* plan);
+int b2d_plan_num_frames(const b2d_plan* plan, int L);     /* T = 1 + L / hop                 */
+int b2d_plan_output_length(const b2d_plan* plan, int T);  /* hop * (T - 1)  (length=None)    */
+int b2d_plan_frame_stride(const b2d_plan* plan);          /* Fp = n_fft/2 + 4                */
+
+/* ---- model ------------------------------------------------------------------------------------
+ * GRUUNet2(num_compressed_bins, in_size=1, hidden_sizes, kernel_sizes, strides, paddings,
+ * num_gaussians) -- gruunet2.py:246-264.  h_params: n_params host pointers in state_dict
+ * `parameters()` order: input_gate.downs.{i}.conv.{weight,bias} (levels),
+ * reset_gate.downs.0.conv.{weight,bias}, output_gate.ups.{i}.conv.{weight,bias} (levels).
+ * h_gs_offsets: 3 host pointers to the `gs.offset` buffers (input, reset, output gate), each
+ * [num_gaussians].  Supported: uniform hidden size <= 32, kernel 3, stride 2, padding 1,
+ * levels in [1, 6]; anything else -> B2D_ERR_UNSUPPORTED. */
+typedef struct {
+  int num_compressed_bins;
+  int hidden;        /* hidden_sizes[i], all equal */
+  int levels;        /* len(hidden_sizes)          */
+  int kernel, stride, padding;
+  int num_gaussians;
+} b2d_model_config;
+
+int b2d_model_create(const b2d_model_config* cfg, const float* const* h_params, int n_params,
+                     const float* const* h_gs_offsets, b2d_model** out);
+void b2d_model_destroy(b2d_model* model);
+int b2d_model_n_mels(const b2d_model* model); /* num_compressed_bins << levels */
+
+/* ---- K0: per-clip peak (app3.py:181-186) ------------------------------------------------------
+ * peak[b] = max|wave[b,:]| if > 1e-6 else 1. */
+int b2d_peak(const float* wave, int B, int L, float* peak, void* stream);
+
+/* ---- K1: Spectrogram(power=None) forward (app3.py:191, server.py:207; TA:functional/functional.py:54-145)
+ * wave [B, L] -> spec [B, F, T] complex (torch layout).  L > n_fft/2 (reflect padding). */
+int b2d_stft(const b2d_plan* plan, const float* wave, int B, int L, b2d_c64* spec, void* stream);
+
+/* ---- K1+K2 fused: log1p(MelScale(|Spectrogram(x)|)) (app3.py:191-193, server.py:207-210) --------
+ * Any of the outputs may be NULL.  logmel_bt [B, T, n_mels] is the model-input layout
+ * (app3.py:195 transposes to it), logmel_bm [B, n_mels, T] is MelScale's own layout, spec as b2d_stft.
+ * inv_scale (nullable, [B]): every sample of clip b is divided by inv_scale[b] first (a1 fused). */
+int b2d_stft_mel_log1p(const b2d_plan* plan, const float* wave, const float* inv_scale, int B, int L,
+                       float* logmel_bt, float* logmel_bm, b2d_c64* spec, void* stream);
+
+/* ---- K2 alone: MelScale.forward (TA:transforms/_transforms.py:407-419): mag [B,F,T] -> mel [B,n_mels,T] */
+int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* mel, void* stream);
+
+/* ---- K3: GRUUNet2.forward (gruunet2.py:290-306) -----------------------------------------------
+ * x [B, T, n_mels], hx [B, hidden, bins] in/out (caller zero-fills it for hx=None), out [B, T, n_mels].
+ * Runs encoder (time-parallel) -> persistent recurrence -> decoder (time-parallel).
+ * conv_mode: 0 = fp32 CUDA-core convolutions (parity mode), 1 = tcgen05 bf16x3 split (tensor cores,
+ * fp32-class accuracy), 2 = tcgen05 plain bf16 (throughput mode). */
+size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T);
+int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T,
+                         int conv_mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: residual + nonlinearity (app3.py:203-208 / server.py:213-215) -------------------------
+ * mode 0 (app):    mel = max(expm1(leaky_relu(x - pred, 0.2)), 0)
+ * mode 1 (server): mel = exp(x - relu(pred) * out_scale) - 1            (out_scale = 3)
+ * x, pred, mel_bt: [B, T, n_mels] (n = B*T*n_mels elements). */
+int b2d_residual_mel(const float* x, const float* pred, float* mel_bt, size_t n, int mode, float out_scale, void* stream);
+
+/* ---- K5: InverseMelScale.forward (TA:transforms/_transforms.py:491-512) = relu(pinv(fb^T) @ mel)
+ * torch layout: mel [B, n_mels, T] -> lin [B, F, T]. */
+int b2d_inverse_mel(const b2d_plan* plan, const float* mel, int B, int T, float* lin, void* stream);
+/* frame layout: mel_bt [B, T, n_mels] -> mag_tf [B, T, Fp] (columns F..Fp-1 are written as 0). */
+int b2d_inverse_mel_frames(const b2d_plan* plan, const float* mel_bt, int B, int T, float* mag_tf, void* stream);
+
+/* ---- K6: GriffinLim(power=1) (app3.py:213; TA:functional/functional.py:255-353) -----------------
+ * mag [B, F, T] torch layout (b2d_griffinlim) or [B, T, Fp] frame layout (b2d_griffinlim_frames);
+ * init_angles [B, F, T] complex torch layout = the `angles` tensor of TA functional.py:309-312
+ * (NULL = rand_init=False, all ones);  momentum is the user-facing value (0.99), rescaled inside as
+ * at TA functional.py:300;  out_scale (nullable, [B]) multiplies clip b's waveform (app3.py:217).
+ * wave [B, hop*(T-1)].  T >= 3. */
+size_t b2d_griffinlim_workspace_bytes(const b2d_plan* plan, int B, int T);
+int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, int B, int T,
+                   int n_iter, float momentum, const float* out_scale, float* wave,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, int B, int T,
+                          int n_iter, float momentum, const float* out_scale, float* wave,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7: InverseSpectrogram / torch.istft (server.py:216; TA:functional/functional.py:205) ------
+ * spec [B, F, T] complex torch layout -> wave [B, hop*(T-1)].  If mag != NULL the spectrum used is
+ * torch.polar(mag, angle(spec)) = mag * spec/|spec| (server.py:216 with phase from :208). */
+int b2d_istft(const b2d_plan* plan, const b2d_c64* spec, const float* mag, int B, int T, float* wave, void* stream);
+
+/* ---- whole chain, app3.py:181-217 applied to whole clips ---------------
+ * noisy [B, L] -> wave [B, hop*(T-1)].  hx [B, hidden, bins] in/out.  normalise != 0 applies the
+ * per-clip peak normalisation of app3.py:181-186 and the final `* peak` of :217.
+ * Optional debug outputs (nullable): logmel_bt, pred_bt [B,T,n_mels], mag_tf [B,T,Fp]. */
+size_t b2d_denoise_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L);
+int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L,
+                      float* hx, const b2d_c64* init_angles, int n_iter, float momentum, int normalise,
+                      int conv_mode, float* wave, float* logmel_bt, float* pred_bt, float* mag_tf,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- server.py:207-216 chain (noisy-phase iSTFT, no Griffin-Lim) --------------------------------
+ * x [B, L] -> wave [B, hop*(T-1)];  hx in/out and multiplied by hx_decay (0.9) afterwards. */
+size_t b2d_denoise_noisy_phase_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L);
+int b2d_denoise_noisy_phase(const b2d_plan* plan, const b2d_model* model, const float* x, int B, int L,
+                            float* hx, float out_scale, float hx_decay, int conv_mode, float* wave,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- streaming hop, app3.py:178-226 (one `while` iteration for S independent sessions) ----------
+ * chunk [S, n_fft] raw float samples (the current input window), hx [S, hidden, bins] in/out,
+ * ola [S, n_fft] in/out output overlap-add ring, out [S, hop] the hop of audio emitted by this step.
+ * init_angles [S, F, 3] or NULL.  compat != 0 keeps quirks Q2-Q4 of SURVEY.md Appendix C. */
+size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int S);
+int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx,
+                    float* ola, const b2d_c64* init_angles, int n_iter, float momentum, int conv_mode,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels this library has launched from the calling process (all threads); bench.py
+ * reports the difference across the timed region as "gpu_launches". */
+unsigned long long b2d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DENOISE_H_ */
