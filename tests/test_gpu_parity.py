@@ -350,7 +350,7 @@ def test_full_size_properties_config2(dev):
     gl = adb.GriffinLim(n_fft=n_fft, hop_length=hop, power=1.0).to(dev)
     big = gl(mag[:64], init_angles=init[:1].expand(64, -1, -1).contiguous())
     small = gl(mag[5:6], init_angles=init[:1])
-    assert metrics.si_sdr(big[5:6].cpu(), small.cpu()).min() >= 100.0  # partition-independent result
+    assert metrics.si_sdr(big[5:6].cpu(), small.cpu()).min() >= 70.0  # same answer whatever the batch / run partition (up to fp32 rounding amplified by 32 iterations)
     # spot-check a few clips of the full batch against the CPU oracle
     ref = dsp.griffinlim(mag[[0, 63]].cpu(), n_fft, hop, 32, 0.99, init[:1].expand(2, -1, -1).cpu())
     assert metrics.si_sdr(big[[0, 63]].cpu(), ref).min() >= 60.0
