@@ -82,12 +82,12 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
   B2D_CUDA(cudaGetDevice(&p->device));
   B2D_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
   const int N = n_fft, M = p->M, F = p->F;
-  std::vector<float2> tw(M), rtw(M / 2 + 1);
+  std::vector<float2> tw(M), rtw(M);  // rtw: W_N^k for k = 0..M-1 (generic kernels use k <= M/2)
   for (int k = 0; k < M; ++k) {
     const double a = -2.0 * M_PI * (double)k / (double)M;
     tw[k] = make_float2((float)cos(a), (float)sin(a));
   }
-  for (int k = 0; k <= M / 2; ++k) {
+  for (int k = 0; k < M; ++k) {
     const double a = -2.0 * M_PI * (double)k / (double)N;
     rtw[k] = make_float2((float)cos(a), (float)sin(a));
   }

@@ -58,7 +58,7 @@ struct b2d_plan {
   int device;
   int num_sms;
   float2* d_tw;       // [M]      W_M^k   = exp(-2 pi i k / M)
-  float2* d_rtw;      // [M/2+1]  W_N^k   = exp(-2 pi i k / N)   (real-FFT split twiddles)
+  float2* d_rtw;      // [M]      W_N^k   = exp(-2 pi i k / N)   (real-FFT split twiddles)
   float* d_win;       // [N]      periodic Hann
   float* d_winn;      // [N]      Hann / N (synthesis window with the irfft 1/N folded in)
   float* d_inv_env;   // [hop]    1 / (w^2[i] + w^2[i+hop])      (valid when hop == N/2)

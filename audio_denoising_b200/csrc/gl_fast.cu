@@ -1,0 +1,256 @@
+// gl_fast.cu -- the n_fft = 1024 Griffin-Lim iteration kernel (see gl_fast.cuh for the data flow).
+#include <stdlib.h>
+
+#include "gl_fast.cuh"
+#include "kernels.cuh"
+
+namespace b2d {
+
+using namespace fast512;
+
+struct GlFastArgs {
+  const float* mag_tf;   // [B,T,Fp]
+  float2* tprev;         // [B,T,M]
+  const float* xin;      // partial hop-block format (run = one warp's frames)
+  float* xout;
+  int B, T, n, R, Fp;
+  const float2* tw512;   // W512^k
+  const float2* rtw;     // W1024^k, k = 0..511
+  const float* win;      // [1024]
+  const float* winn;     // [1024] win / N
+  const float* inv_env;  // [512]
+  float mom;
+  int use_prev, store_prev;
+};
+
+// ---- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// per-warp shared-memory staging: exchange buffer | tprev row | mag row | mbarrier
+constexpr int MAG_ROW_BYTES = (M + 4) * 4;                      // Fp floats = 2064 B
+constexpr int WARP_SMEM = XCH * 8 + M * 8 + 2080 + 16;          // 10800 B, 16-byte multiple
+
+// same partial-format helpers as the generic kernel (griffinlim.cu); only used for the two reflect-padded
+// edge blocks of a clip (j == 0 and j == T), through a compact non-unrolled loop
+__device__ __noinline__ void stage_reflect_block(const float* __restrict__ part, const float* __restrict__ inv_env,
+                                                  const float* __restrict__ win_half, int b, int R, int n, int T, int j,
+                                                  float* __restrict__ dst, int lane) {
+  for (int i = lane; i < HOP; i += 32) {
+    int js, is;
+    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
+    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
+    const int r1 = (js - 1) / n, r2 = js / n;
+    float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
+    if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
+    dst[i] = v * inv_env[is] * win_half[i];
+  }
+}
+
+template <int WARPS, int MINB, bool USE_PREV>
+__global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFastArgs a) {
+  // tables (float2 views): WA[256] = inv_env*win (first half), WB[256] = inv_env*win (second half),
+  // WN[512] = win/N, RT[512] = W1024^k ; per-warp exchange buffers behind them
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WA = reinterpret_cast<float2*>(smem_raw);
+  float2* WB = WA + 256;
+  float2* WN = WB + 256;
+  float2* RT = WN + 512;
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + 512);
+
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
+    WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WARPS + warp;
+  if (gw >= a.B * a.R) return;
+  const int b = gw / a.R, r = gw - b * a.R;
+  const int n = a.n, R = a.R, T = a.T;
+  const int tb = r * n, te = min(T, tb + n);
+  unsigned char* wsm = warp_base + (size_t)warp * WARP_SMEM;
+  float2* S = reinterpret_cast<float2*>(wsm);                       // exchange buffer
+  float2* tp_s = reinterpret_cast<float2*>(wsm + XCH * 8);          // staged tprev row of the current frame
+  float* mg_s = reinterpret_cast<float*>(wsm + XCH * 8 + M * 8);    // staged mag row
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + XCH * 8 + M * 8 + 2080);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  LaneTw tw;
+  lane_twiddles(lane, a.tw512, tw);
+  // lane 0 owns families 0 and 32: its slots r >= 4 sit 224 bins below the regular lane + 64 r pattern
+  const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
+
+  const size_t run_stride = (size_t)(n + 1) * HOP;
+  const float* xrun = a.xin + (size_t)(b * R + r) * run_stride;
+  float* xo = a.xout + (size_t)(b * R + r) * run_stride;
+  float2 carry[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
+
+  const uint32_t row_bytes = MAG_ROW_BYTES + (USE_PREV ? M * 8 : 0);
+  if (lane == 0) {  // TMA: rows of the first frame
+    mbar_expect_tx(bar, row_bytes);
+    bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, MAG_ROW_BYTES, bar);
+    if (USE_PREV) bulk_g2s(tp_s, a.tprev + ((size_t)b * T + tb) * M, M * 8, bar);
+  }
+#pragma unroll 1
+  for (int t = tb; t < te; ++t) {
+    const int c = t - tb;
+    float2 v[16];
+    if (t + 2 < te && lane < 16) prefetch_l2(xrun + (size_t)(c + 2) * HOP + lane * 32);  // next frame's new hop-block
+    // ---- stage the frame: hop-blocks t (first half) and t+1 (second half), envelope + window applied ---
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = t + h;            // padded hop-block index
+      const int cs = c + h;           // slot inside this run
+      const float2* wtab = h ? WB : WA;
+      if (j == 0 || j == T) {          // reflect-padded edge of the clip (2 blocks per clip): generic path via smem
+        __syncwarp();
+        stage_reflect_block(a.xin, a.inv_env, a.win + h * HOP, b, R, n, T, j, reinterpret_cast<float*>(S), lane);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[8 * h + q] = S[lane + 32 * q];
+      } else {
+        const float2* p1 = reinterpret_cast<const float2*>(xrun + (size_t)cs * HOP);
+        const float2* p2 = nullptr;   // second partial when the block sits on a run boundary
+        if (cs == 0) p2 = reinterpret_cast<const float2*>(xrun - run_stride + (size_t)n * HOP);   // previous run, last slot
+        else if (j == te) p2 = reinterpret_cast<const float2*>(xrun + run_stride);                // next run, slot 0
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float2 xv = p1[lane + 32 * q];
+          if (p2) { const float2 x2 = p2[lane + 32 * q]; xv.x += x2.x; xv.y += x2.y; }
+          const float2 wv = wtab[lane + 32 * q];
+          v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
+      }
+    }
+    // ---- forward FFT ------------------------------------------------------------------------------------
+    __syncwarp();
+    fwd1_store(lane, v, tw, S);
+    __syncwarp();
+    fwd2_load(lane, v, S);
+    __syncwarp();
+    fwd2_store(lane, v, tw, S);
+    __syncwarp();
+    fwd3_load(lane, v, S);
+    // ---- spectral update (tprev / mag rows were bulk-copied into smem one frame ahead) -----------------------
+    float2* tp = a.tprev + ((size_t)b * T + t) * M;
+    mbar_wait(bar, c & 1);
+    if (lane == 0) lane0_permute(v);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int k = (rr < 4 ? kU0 : kU4) + 64 * rr;
+      float2& U = v[2 * rr];
+      float2& V = v[2 * (7 - rr) + 1];
+      if (rr == 0 && lane == 0) {
+        float2 x0M, x256;
+        special_update(U, V, USE_PREV ? tp_s[0] : make_float2(0.f, 0.f), USE_PREV ? tp_s[256] : make_float2(0.f, 0.f), mg_s[0], mg_s[M],
+                       mg_s[256], a.mom, USE_PREV, x0M, x256);
+        if (a.store_prev) { __stcs(tp, x0M); __stcs(tp + 256, x256); }
+      } else {
+        float2 xk, xmk;
+        pair_update(U, V, RT[k], USE_PREV ? tp_s[k] : make_float2(0.f, 0.f), USE_PREV ? tp_s[(M - k) & (M - 1)] : make_float2(0.f, 0.f),
+                    mg_s[k], mg_s[M - k], a.mom, USE_PREV, xk, xmk);
+        if (a.store_prev) { __stcs(tp + k, xk); __stcs(tp + (M - k), xmk); }
+      }
+    }
+    __syncwarp();  // every lane is done reading the staged rows
+    if (lane == 0 && t + 1 < te) {  // TMA: rows of the next frame land while this frame's inverse FFT runs
+      mbar_expect_tx(bar, row_bytes);
+      bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + t + 1) * a.Fp, MAG_ROW_BYTES, bar);
+      if (USE_PREV) bulk_g2s(tp_s, a.tprev + ((size_t)b * T + t + 1) * M, M * 8, bar);
+    }
+    if (lane == 0) lane0_unpermute(v);
+    // ---- inverse FFT ------------------------------------------------------------------------------------
+    __syncwarp();
+    inv1_store(lane, v, S);
+    __syncwarp();
+    inv2_load(lane, v, tw, S);
+    __syncwarp();
+    inv2_store(lane, v, S);
+    __syncwarp();
+    inv3_load(lane, v, tw, S);
+    // ---- synthesis window + overlap-add: block c = carry + first half ; carry = second half --------------
+    float2* dst = reinterpret_cast<float2*>(xo + (size_t)c * HOP);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
+      dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
+      carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+    }
+  }
+  float2* dst = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[lane + 32 * q] = carry[q];
+}
+
+template <int WARPS, int MINB>
+static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
+  const int runs = a.B * a.R;
+  const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)WARPS * WARP_SMEM;
+  const dim3 grid((runs + WARPS - 1) / WARPS), block(WARPS * 32);
+  if (a.use_prev) {
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, true><<<grid, block, smem, st>>>(a);
+  } else {
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, false><<<grid, block, smem, st>>>(a);
+  }
+  B2D_LAUNCH_CHECK("gl_fast512_kernel");
+  return B2D_OK;
+}
+
+int gl_fast_warps_per_sm() {
+  const char* e = getenv("B2D_GL_VARIANT");
+  const int v = e ? atoi(e) : 0;
+  return v == 1 ? 12 : 16;
+}
+
+int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
+                      int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st) {
+  GlFastArgs a;
+  a.mag_tf = mag_tf; a.tprev = tprev; a.xin = xin; a.xout = xout;
+  a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
+  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev;
+  const char* e = getenv("B2D_GL_VARIANT");
+  const int variant = e ? atoi(e) : 0;
+  if (variant == 1) return launch_variant<4, 3>(a, st);   // 12 warps/SM, up to 168 registers
+  if (variant == 2) return launch_variant<4, 4>(a, st);   // 16 warps/SM in 4-warp CTAs
+  return launch_variant<8, 2>(a, st);                     // 16 warps/SM in 8-warp CTAs
+}
+
+}  // namespace b2d

@@ -15,6 +15,8 @@
 // restricted to the frames of that run.  A hop-block on a run boundary is the sum of two slots
 // (x_block_sample).  The window-envelope division and the reflect padding of torch.stft are applied
 // when the next iteration stages its input.
+#include <stdlib.h>
+
 #include "fft.cuh"
 #include "kernels.cuh"
 
@@ -200,10 +202,25 @@ __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
+                      int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast.cu
+int gl_fast_warps_per_sm();
+
 GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   GlPartition q;
   q.G = (p->M <= 1024) ? 4 : 2;
-  q.fast = false;
+  q.fast = (p->n_fft == 1024 && p->hop == 512 && getenv("B2D_GL_GENERIC") == nullptr);
+  if (q.fast) {
+    // one warp per run; 16 warps resident per SM (2 CTAs x 8 warps): aim for a single, nearly full wave
+    const long slots = (long)gl_fast_warps_per_sm() * p->num_sms;
+    int R = (int)(slots / B);
+    if (R < 1) R = 1;
+    const int maxR = (T + 3) / 4;  // at least 4 frames per run
+    if (R > maxR) R = maxR;
+    q.n = (T + R - 1) / R;
+    q.R = (T + q.n - 1) / q.n;
+    return q;
+  }
   const int target = 4 * p->num_sms;  // CTAs wanted in flight
   int R = (target + B - 1) / B;
   const int maxR = (T + q.G - 1) / q.G;
@@ -263,8 +280,13 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, in
     a.use_prev = (it > 0 && a.mom != 0.f) ? 1 : 0;
     a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
     a.xin = cur; a.xout = nxt;
-    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
-    B2D_LAUNCH_CHECK("gl_generic_kernel");
+    if (q.fast) {
+      int rc = launch_gl_fast512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
+      if (rc != B2D_OK) return rc;
+    } else {
+      gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+      B2D_LAUNCH_CHECK("gl_generic_kernel");
+    }
     float* t = cur; cur = nxt; nxt = t;
   }
   gl_stitch_kernel<<<dim3(T - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop);

@@ -1,0 +1,122 @@
+// CPU emulation of one warp of the n_fft=1024 fast Griffin-Lim path (csrc/gl_fast.cuh): checks the
+// three-pass register/shared-memory data flow against a naive DFT, and the lane-local spectral update
+// against a straightforward double-precision evaluation of one Griffin-Lim iteration on one frame.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <vector>
+#include "../../audio_denoising_b200/csrc/gl_fast.cuh"
+using namespace b2d;
+using namespace b2d::fast512;
+typedef std::complex<double> cd;
+
+static float frand(unsigned& s) { s = s * 1664525u + 1013904223u; return (s >> 8) / 16777216.0f - 0.5f; }
+
+int main() {
+  int bad = 0;
+  std::vector<float2> tw(M), rt(M);
+  for (int k = 0; k < M; ++k) {
+    tw[k] = make_float2((float)cos(-2 * M_PI * k / M), (float)sin(-2 * M_PI * k / M));
+    rt[k] = make_float2((float)cos(-2 * M_PI * k / N), (float)sin(-2 * M_PI * k / N));
+  }
+  LaneTw lt[32];
+  for (int l = 0; l < 32; ++l) lane_twiddles(l, tw.data(), lt[l]);
+  unsigned seed = 7;
+  std::vector<float> x(N);
+  for (auto& v : x) v = frand(seed);
+  std::vector<float2> z(M);
+  for (int m = 0; m < M; ++m) z[m] = make_float2(x[2 * m], x[2 * m + 1]);
+  std::vector<cd> Z(M);
+  for (int k = 0; k < M; ++k) { cd a = 0; for (int m = 0; m < M; ++m) a += cd(z[m].x, z[m].y) * std::polar(1.0, -2 * M_PI * (double)((long)m * k % M) / M); Z[k] = a; }
+
+  float2 v[32][16];
+  std::vector<float2> S(XCH);
+  auto forward = [&]() {
+    for (int l = 0; l < 32; ++l) fwd1_store(l, v[l], lt[l], S.data());
+    for (int l = 0; l < 32; ++l) fwd2_load(l, v[l], S.data());
+    for (int l = 0; l < 32; ++l) fwd2_store(l, v[l], lt[l], S.data());
+    for (int l = 0; l < 32; ++l) fwd3_load(l, v[l], S.data());
+  };
+  auto inverse = [&]() {
+    for (int l = 0; l < 32; ++l) inv1_store(l, v[l], S.data());
+    for (int l = 0; l < 32; ++l) inv2_load(l, v[l], lt[l], S.data());
+    for (int l = 0; l < 32; ++l) inv2_store(l, v[l], S.data());
+    for (int l = 0; l < 32; ++l) inv3_load(l, v[l], lt[l], S.data());
+  };
+  for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) v[l][q] = z[l + 32 * q];
+  forward();
+  double e = 0, nrm = 0;
+  std::vector<int> seen(M, 0);
+  for (int l = 0; l < 32; ++l) for (int f = 0; f < 2; ++f) for (int k3 = 0; k3 < 8; ++k3) {
+    int k = fam(l, f) + 64 * k3; seen[k]++;
+    e += std::norm(cd(v[l][2 * k3 + f].x, v[l][2 * k3 + f].y) - Z[k]); nrm += std::norm(Z[k]);
+  }
+  for (int k = 0; k < M; ++k) if (seen[k] != 1) { printf("bin %d covered %d times\n", k, seen[k]); bad++; }
+  printf("forward rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 2e-6) bad++;
+  inverse();
+  e = 0; nrm = 0;
+  for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) {
+    cd want = 512.0 * cd(z[l + 32 * q].x, z[l + 32 * q].y);
+    e += std::norm(cd(v[l][q].x, v[l][q].y) - want); nrm += std::norm(want);
+  }
+  printf("round trip rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 2e-6) bad++;
+
+  // ---- one full frame iteration: window omitted (x is the already windowed frame) ----
+  std::vector<float2> P(M);      // previous rebuilt, packed slot 0 = (Re P0, Re PM)
+  std::vector<float> mag(M + 4);
+  for (int k = 0; k < M; ++k) P[k] = make_float2(20 * frand(seed), 20 * frand(seed));
+  for (int k = 0; k <= M; ++k) mag[k] = 3.0f * (frand(seed) + 0.5f);
+  const float mom = 0.99f / 1.99f;
+  // reference in double
+  std::vector<cd> X(M + 1), Y(M + 1);
+  for (int k = 0; k <= M; ++k) { cd a = 0; for (int n = 0; n < N; ++n) a += (double)x[n] * std::polar(1.0, -2 * M_PI * (double)((long)n * k % N) / N); X[k] = a; }
+  for (int k = 0; k <= M; ++k) {
+    cd p = (k == 0) ? cd(P[0].x, 0) : (k == M) ? cd(P[0].y, 0) : cd(P[k].x, P[k].y);
+    cd a = X[k] - (double)mom * p;
+    if (k == 0 || k == M) a = cd(a.real(), 0);
+    Y[k] = (double)mag[k] * a / (std::abs(a) + 1e-16);
+  }
+  std::vector<double> yref(N);
+  for (int n = 0; n < N; ++n) {
+    cd a = Y[0].real() + Y[M].real() * ((n & 1) ? -1.0 : 1.0);
+    for (int k = 1; k < M; ++k) a += 2.0 * (Y[k] * std::polar(1.0, 2 * M_PI * (double)((long)n * k % N) / N)).real();
+    yref[n] = a.real();  // = N * irfft(Y)
+  }
+  for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) v[l][q] = z[l + 32 * q];
+  forward();
+  std::vector<float2> newP(M, make_float2(0, 0));
+  std::vector<int> stored(M, 0);
+  for (int l = 0; l < 32; ++l) {
+    if (l == 0) lane0_permute(v[l]);
+    for (int r = 0; r < 8; ++r) {
+      const int k = slot_k(l, r);
+      float2& U = v[l][2 * r];
+      float2& V = v[l][2 * (7 - r) + 1];
+      if (l == 0 && r == 0) {
+        float2 x0M, x256;
+        special_update(U, V, P[0], P[256], mag[0], mag[M], mag[256], mom, true, x0M, x256);
+        newP[0] = x0M; newP[256] = x256; stored[0]++; stored[256]++;
+      } else {
+        float2 xk, xmk;
+        pair_update(U, V, rt[k], P[k], P[M - k], mag[k], mag[M - k], mom, true, xk, xmk);
+        newP[k] = xk; newP[M - k] = xmk; stored[k]++; stored[M - k]++;
+      }
+    }
+    if (l == 0) lane0_unpermute(v[l]);
+  }
+  for (int k = 0; k < M; ++k) if (stored[k] != 1) { printf("tprev bin %d stored %d times\n", k, stored[k]); bad++; }
+  e = 0; nrm = 0;
+  for (int k = 1; k < M; ++k) { e += std::norm(cd(newP[k].x, newP[k].y) - X[k]); nrm += std::norm(X[k]); }
+  e += std::norm(cd(newP[0].x, 0) - X[0]) + std::norm(cd(newP[0].y, 0) - X[M]);
+  printf("rebuilt (tprev) rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 2e-6) bad++;
+  inverse();
+  e = 0; nrm = 0;
+  for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) {
+    int m = l + 32 * q;
+    e += pow(v[l][q].x - yref[2 * m], 2) + pow(v[l][q].y - yref[2 * m + 1], 2);
+    nrm += pow(yref[2 * m], 2) + pow(yref[2 * m + 1], 2);
+  }
+  printf("frame iteration rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 5e-6) bad++;
+  printf(bad ? "FAIL\n" : "OK\n");
+  return bad;
+}
