@@ -34,7 +34,7 @@ class ModelConfig(C.Structure):
     ]
 
 
-_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_vp, _i, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
 
 # name -> (restype, argtypes); mirrors include/b200denoise.h one to one
 SIGNATURES = {
@@ -59,15 +59,15 @@ SIGNATURES = {
     "b2d_inverse_mel": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2d_inverse_mel_frames": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2d_griffinlim_workspace_bytes": (_sz, [_vp, _i, _i]),
-    "b2d_griffinlim": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
-    "b2d_griffinlim_frames": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "b2d_griffinlim": (_i, [_vp, _vp, _vp, _u64, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "b2d_griffinlim_frames": (_i, [_vp, _vp, _vp, _u64, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "b2d_istft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b2d_denoise_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
-    "b2d_denoise_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2d_denoise_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _u64, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2d_denoise_noisy_phase_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
     "b2d_denoise_noisy_phase": (_i, [_vp, _vp, _vp, _i, _i, _vp, _f, _f, _i, _vp, _vp, _sz, _vp]),
     "b2d_stream_step_workspace_bytes": (_sz, [_vp, _vp, _i]),
-    "b2d_stream_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _i, _vp, _vp, _sz, _vp]),
+    "b2d_stream_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _u64, _i, _f, _i, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

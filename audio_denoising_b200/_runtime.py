@@ -126,6 +126,11 @@ class Workspace:
         return self._buf
 
 
+def draw_seed() -> int:
+    """Non-zero 62-bit seed for the in-kernel Griffin-Lim initial-phase draws, taken from torch's CPU generator."""
+    return int(torch.randint(1, 2**62, (1,), dtype=torch.int64).item())
+
+
 def is_hann(window_fn, win_length: int, wkwargs=None) -> bool:
     if window_fn is torch.hann_window and not wkwargs:
         return True

@@ -28,8 +28,8 @@ int model_pack(b2d_model* m, const float* const* hp, const float* const* offs); 
 bool model_config_supported(const b2d_model_config* c);
 int model_pack_tc(b2d_model* m);  // conv_tc.cu
 int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
-                     const float2* init_angles, int n_iter, float momentum, int conv_mode, float* out, void* ws,
-                     size_t ws_bytes, cudaStream_t st);  // stream.cu
+                     const float2* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
+                     void* ws, size_t ws_bytes, cudaStream_t st);  // stream.cu
 size_t stream_step_ws(const b2d_plan* p, const b2d_model* m, int S);
 
 static bool factor(int M, FftDesc& fd) {
@@ -252,16 +252,17 @@ size_t b2d_griffinlim_workspace_bytes(const b2d_plan* plan, int B, int T) {
   if (!plan || B < 1 || T < 3) return 0;
   return gl_workspace_bytes(plan, B, T, true);
 }
-int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, int B, int T, int n_iter,
-                          float momentum, const float* out_scale, float* wave, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, unsigned long long seed, int B,
+                          int T, int n_iter, float momentum, const float* out_scale, float* wave, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   B2D_REQUIRE(plan && mag_tf && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
   B2D_REQUIRE(aligned16(mag_tf) && aligned16(workspace), B2D_ERR_ALIGN, "mag_tf / workspace must be 16-byte aligned");
-  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, out_scale, wave, workspace,
-                workspace_bytes, ST(stream));
+  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum, out_scale, wave,
+                workspace, workspace_bytes, ST(stream));
 }
-int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, int B, int T, int n_iter, float momentum,
-                   const float* out_scale, float* wave, void* workspace, size_t workspace_bytes, void* stream) {
+int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, unsigned long long seed, int B, int T,
+                   int n_iter, float momentum, const float* out_scale, float* wave, void* workspace, size_t workspace_bytes,
+                   void* stream) {
   B2D_REQUIRE(plan && mag && wave && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
   CHECK_BATCH(B);
   B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
@@ -271,8 +272,8 @@ int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_a
   float* mag_tf = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + core);
   int rc = launch_to_frame_layout(mag, mag_tf, B, plan->F, T, plan->Fp, ST(stream));
   if (rc) return rc;
-  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, out_scale, wave, workspace,
-                core, ST(stream));
+  return gl_run(plan, mag_tf, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum, out_scale, wave,
+                workspace, core, ST(stream));
 }
 
 int b2d_istft(const b2d_plan* plan, const b2d_c64* spec, const float* mag, int B, int T, float* wave, void* stream) {
@@ -285,6 +286,7 @@ int b2d_istft(const b2d_plan* plan, const b2d_c64* spec, const float* mag, int B
 
 // ---- whole chains -----------------------------------------------------------------------------
 // workspace: peak[B] | logmel[B,T,M] | pred[B,T,M] | mel[B,T,M] | mag_tf[B,T,Fp] | model ws | GL ws
+constexpr int kPeakChunks = 16;
 struct ChainWs {
   float *peak, *logmel, *pred, *mel, *mag;
   unsigned char* model_ws; size_t model_bytes;
@@ -297,7 +299,7 @@ static ChainWs chain_layout(const b2d_plan* p, const b2d_model* m, int B, int T,
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return q ? q + at : nullptr; };
   const size_t nm = (size_t)B * T * p->n_mels * sizeof(float);
-  w.peak = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
+  w.peak = reinterpret_cast<float*>(take((size_t)B * (1 + kPeakChunks) * sizeof(float)));  // peak[B] | partial[B, chunks]
   w.logmel = reinterpret_cast<float*>(take(nm));
   w.pred = reinterpret_cast<float*>(take(nm));
   w.mel = reinterpret_cast<float*>(take(nm));
@@ -323,7 +325,8 @@ size_t b2d_denoise_workspace_bytes(const b2d_plan* plan, const b2d_model* model,
 }
 
 int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L, float* hx,
-                      const b2d_c64* init_angles, int n_iter, float momentum, int normalise, int conv_mode, float* wave,
+                      const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int normalise,
+                      int conv_mode, float* wave,
                       float* logmel_bt, float* pred_bt, float* mag_tf, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_stft_args(plan, noisy, B, L);
   if (rc) return rc;
@@ -338,12 +341,12 @@ int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float*
   float* logmel = logmel_bt ? logmel_bt : w.logmel;
   float* pred = pred_bt ? pred_bt : w.pred;
   float* mag = mag_tf ? mag_tf : w.mag;
-  if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak, 1, st))) return rc;
+  if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
   if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
   if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) return rc;
-  return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), B, T, n_iter, momentum, normalise ? w.peak : nullptr, wave,
-                w.gl_ws, w.gl_bytes, st);
+  return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum,
+                normalise ? w.peak : nullptr, wave, w.gl_ws, w.gl_bytes, st);
 }
 
 size_t b2d_denoise_noisy_phase_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L) {
@@ -387,10 +390,10 @@ size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* mo
   return stream_step_ws(plan, model, S);
 }
 int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx, float* ola,
-                    const b2d_c64* init_angles, int n_iter, float momentum, int conv_mode, float* out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
   B2D_REQUIRE(plan && model && chunk && hx && ola && out && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
-  return stream_step_impl(plan, model, chunk, S, hx, ola, reinterpret_cast<const float2*>(init_angles), n_iter, momentum,
+  return stream_step_impl(plan, model, chunk, S, hx, ola, reinterpret_cast<const float2*>(init_angles), seed, n_iter, momentum,
                           conv_mode, out, workspace, workspace_bytes, ST(stream));
 }
 

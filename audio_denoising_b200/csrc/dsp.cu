@@ -1,5 +1,7 @@
 // dsp.cu -- K0 peak, K1/K2 STFT (+Mel+log1p), K2 MelScale, K4 residual, K5 inverse Mel, K7 iSTFT.
 // Generic over every supported n_fft (shared-memory Stockham FFT, fft.cuh).
+#include <stdlib.h>
+
 #include "fft.cuh"
 #include "kernels.cuh"
 
@@ -352,8 +354,14 @@ int launch_peak(const float* wave, int B, int L, float* peak, float* partial, in
   return B2D_OK;
 }
 
+int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
+                        cudaStream_t st);  // gl_fast.cu
+
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                 float* logmel_bm, float2* spec, cudaStream_t st) {
+  if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 &&
+      getenv("B2D_STFT_GENERIC") == nullptr)
+    return launch_stft_fast512(p, wave, inv_scale, B, L, logmel_bt, st);
   StftArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.G = frames_per_block(p);
   a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.n_mels = p->n_mels; a.fd = p->fft;

@@ -115,6 +115,17 @@ B2D_HD void dft5(float2* v) {
   v[3] = csub(p2, r);
 }
 
+// Counter-based uniform draw for the Griffin-Lim initial angles (rand_init=True, TA:functional/functional.py:310
+// draws real and imaginary parts ~ U[0,1)): splitmix64 of (seed, element index) -> two 24-bit mantissas.
+B2D_HD float2 rand_angle(unsigned long long seed, unsigned long long idx) {
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  const float k = 1.0f / 16777216.0f;
+  return make_float2((float)((unsigned)(x >> 40)) * k, (float)((unsigned)(x >> 8) & 0xFFFFFFu) * k);
+}
+
 // One radix-R Stockham butterfly: work item w in [0, rows * M/R) of a pass over `rows` independent
 // length-M rows (row stride ld, in float2).  tw[k] = exp(-2 pi i k / M) (forward table; conjugated
 // on the fly for INV).  Host-callable so the index math is unit-tested on the CPU.

@@ -217,6 +217,245 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   for (int q = 0; q < 8; ++q) dst[lane + 32 * q] = carry[q];
 }
 
+// ------------------------------------------------------------------------------------------------
+// x_0 = istft(mag * angles_0) for rand_init (in-kernel counter-based draws) or all-ones angles:
+// the inverse half of the iteration kernel (merge -> inverse FFT -> overlap-add), mag rows via TMA.
+// ------------------------------------------------------------------------------------------------
+struct GlInitArgs {
+  const float* mag_tf;
+  float* xout;
+  int B, T, n, R, Fp;
+  const float2* tw512;
+  const float2* rtw;
+  const float* winn;
+  unsigned long long seed;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const GlInitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WN = reinterpret_cast<float2*>(smem_raw);
+  float2* RT = WN + 512;
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + 512);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WARPS + warp;
+  if (gw >= a.B * a.R) return;
+  const int b = gw / a.R, r = gw - b * a.R;
+  const int n = a.n, R = a.R, T = a.T;
+  const int tb = r * n, te = min(T, tb + n);
+  unsigned char* wsm = warp_base + (size_t)warp * WARP_SMEM;
+  float2* S = reinterpret_cast<float2*>(wsm);
+  float* mg_s = reinterpret_cast<float*>(wsm + XCH * 8 + M * 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + XCH * 8 + M * 8 + 2080);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  LaneTw tw;
+  lane_twiddles(lane, a.tw512, tw);
+  const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
+  float* xo = a.xout + (size_t)(b * R + r) * (size_t)(n + 1) * HOP;
+  float2 carry[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
+  if (lane == 0) {
+    mbar_expect_tx(bar, MAG_ROW_BYTES);
+    bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, MAG_ROW_BYTES, bar);
+  }
+#pragma unroll 1
+  for (int t = tb; t < te; ++t) {
+    const int c = t - tb;
+    float2 v[16];
+    const unsigned long long base = ((unsigned long long)b * T + t) * (M + 1);
+    mbar_wait(bar, c & 1);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int k = (rr < 4 ? kU0 : kU4) + 64 * rr;
+      float2& U = v[2 * rr];
+      float2& V = v[2 * (7 - rr) + 1];
+      const float2 one = make_float2(1.f, 0.f);
+      if (rr == 0 && lane == 0) {
+        const float2 a0 = a.seed ? rand_angle(a.seed, base) : one, aM = a.seed ? rand_angle(a.seed, base + M) : one;
+        const float2 a256 = a.seed ? rand_angle(a.seed, base + 256) : one;
+        const float y0 = mg_s[0] * a0.x, yM = mg_s[M] * aM.x, m256 = mg_s[256];
+        U = make_float2(y0 + yM, y0 - yM);
+        V = make_float2(2.0f * m256 * a256.x, -2.0f * m256 * a256.y);
+      } else {
+        const float2 ak = a.seed ? rand_angle(a.seed, base + k) : one, amk = a.seed ? rand_angle(a.seed, base + (M - k)) : one;
+        const float mk = mg_s[k], mmk = mg_s[M - k];
+        irfft_merge(make_float2(mk * ak.x, mk * ak.y), make_float2(mmk * amk.x, mmk * amk.y), RT[k], U, V);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && t + 1 < te) {
+      mbar_expect_tx(bar, MAG_ROW_BYTES);
+      bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + t + 1) * a.Fp, MAG_ROW_BYTES, bar);
+    }
+    if (lane == 0) lane0_unpermute(v);
+    inv1_store(lane, v, S);
+    __syncwarp();
+    inv2_load(lane, v, tw, S);
+    __syncwarp();
+    inv2_store(lane, v, S);
+    __syncwarp();
+    inv3_load(lane, v, tw, S);
+    float2* dst = reinterpret_cast<float2*>(xo + (size_t)c * HOP);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
+      dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
+      carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+    }
+  }
+  float2* dst = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[lane + 32 * q] = carry[q];
+}
+
+int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
+                           cudaStream_t st) {
+  GlInitArgs a;
+  a.mag_tf = mag_tf; a.xout = xout; a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
+  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed;
+  constexpr int W = 8;
+  const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
+  B2D_CUDA(cudaFuncSetAttribute(gl_fast512_init_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gl_fast512_init_kernel<W><<<(B * R + W - 1) / W, W * 32, smem, st>>>(a);
+  B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2 for n_fft = 1024, hop = 512: one warp per frame -- window, register FFT, |.|, mel, log1p.
+// ------------------------------------------------------------------------------------------------
+struct StftFastArgs {
+  const float* wave;
+  const float* inv_scale;
+  int B, L, T, n_mels;
+  const float2* tw512;
+  const float2* rtw;
+  const float* win;
+  const int* mel_lo;
+  const int* mel_cnt;
+  const int* mel_off;
+  const float* mel_w;
+  int mel_nnz;
+  float* logmel_bt;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) stft_fast512_kernel(const StftFastArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WIN = reinterpret_cast<float2*>(smem_raw);  // [512] plain window pairs
+  float2* RT = WIN + 512;
+  float* melw = reinterpret_cast<float*>(RT + 512);   // [mel_nnz rounded up to 4]
+  float2* xch_all = reinterpret_cast<float2*>(melw + ((a.mel_nnz + 3) & ~3));
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    WIN[i] = make_float2(a.win[2 * i], a.win[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  for (int i = threadIdx.x; i < a.mel_nnz; i += blockDim.x) melw[i] = a.mel_w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* S = xch_all + warp * XCH;
+  float* Sf = reinterpret_cast<float*>(S);
+  LaneTw tw;
+  lane_twiddles(lane, a.tw512, tw);
+  const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
+  const size_t nframes = (size_t)a.B * a.T;
+  const bool even = (a.L & 1) == 0;
+#pragma unroll 1
+  for (size_t f = (size_t)blockIdx.x * WARPS + warp; f < nframes; f += (size_t)gridDim.x * WARPS) {
+    const int b = (int)(f / a.T), t = (int)(f - (size_t)b * a.T);
+    const float* x = a.wave + (size_t)b * a.L;
+    const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
+    const long s0 = (long)t * HOP - HOP;  // first sample of the frame in clip coordinates
+    float2 v[16];
+    if (even && s0 >= 0 && s0 + N <= a.L) {
+      const float2* src = reinterpret_cast<const float2*>(x + s0);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 xv = src[lane + 32 * q];
+        const float2 wv = WIN[lane + 32 * q];
+        v[q] = make_float2((xv.x / sc) * wv.x, (xv.y / sc) * wv.y);
+      }
+    } else {  // reflect-padded edges (or odd L): stage through shared memory
+      __syncwarp();
+      for (int i = lane; i < N; i += 32) {
+        long s = s0 + i;
+        if (s < 0) s = -s;
+        if (s >= a.L) s = 2L * (a.L - 1) - s;
+        Sf[i] = (s >= 0 && s < a.L) ? x[s] / sc : 0.f;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 xv = S[lane + 32 * q];
+        const float2 wv = WIN[lane + 32 * q];
+        v[q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+      }
+    }
+    __syncwarp();
+    fwd1_store(lane, v, tw, S);
+    __syncwarp();
+    fwd2_load(lane, v, S);
+    __syncwarp();
+    fwd2_store(lane, v, tw, S);
+    __syncwarp();
+    fwd3_load(lane, v, S);
+    __syncwarp();  // exchange buffer is re-used for the magnitudes
+    if (lane == 0) lane0_permute(v);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int k = (rr < 4 ? kU0 : kU4) + 64 * rr;
+      const float2 U = v[2 * rr], V = v[2 * (7 - rr) + 1];
+      if (rr == 0 && lane == 0) {
+        Sf[0] = fabsf(U.x + U.y);
+        Sf[M] = fabsf(U.x - U.y);
+        Sf[256] = sqrtf(V.x * V.x + V.y * V.y);
+      } else {
+        float2 xk, xmk;
+        rfft_split(U, V, RT[k], xk, xmk);
+        Sf[k] = sqrtf(xk.x * xk.x + xk.y * xk.y);
+        Sf[M - k] = sqrtf(xmk.x * xmk.x + xmk.y * xmk.y);
+      }
+    }
+    __syncwarp();
+    for (int m = lane; m < a.n_mels; m += 32) {
+      const int lo = a.mel_lo[m], cnt = a.mel_cnt[m];
+      const float* w = melw + a.mel_off[m];
+      float acc = 0.f;
+      for (int q = 0; q < cnt; ++q) acc = fmaf(Sf[lo + q], w[q], acc);
+      a.logmel_bt[f * a.n_mels + m] = log1pf(acc);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
+                        cudaStream_t st) {
+  StftFastArgs a;
+  a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.n_mels = p->n_mels;
+  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win;
+  a.mel_lo = p->d_mel_lo; a.mel_cnt = p->d_mel_cnt; a.mel_off = p->d_mel_off; a.mel_w = p->d_mel_w; a.mel_nnz = p->mel_nnz;
+  a.logmel_bt = logmel_bt;
+  constexpr int W = 8;
+  const size_t smem = sizeof(float2) * 1024 + sizeof(float) * ((p->mel_nnz + 3) & ~3) + sizeof(float2) * (size_t)W * XCH;
+  B2D_CUDA(cudaFuncSetAttribute(stft_fast512_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t nframes = (size_t)B * a.T;
+  const size_t want = (nframes + W - 1) / W;
+  const int grid = (int)(want < (size_t)p->num_sms * 2 ? want : (size_t)p->num_sms * 2);
+  stft_fast512_kernel<W><<<grid, W * 32, smem, st>>>(a);
+  B2D_LAUNCH_CHECK("stft_fast512_kernel");
+  return B2D_OK;
+}
+
 template <int WARPS, int MINB>
 static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
   const int runs = a.B * a.R;

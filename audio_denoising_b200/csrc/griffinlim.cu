@@ -38,6 +38,7 @@ struct GlArgs {
   const float* inv_env;
   float mom;
   int init, use_prev, store_prev;
+  unsigned long long seed;  // init only: angles0 == null and seed != 0 -> in-kernel uniform draws
 };
 
 // normalised interior hop-block sample, 1 <= j <= T-1
@@ -165,6 +166,11 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
             const float2 amk = a.angles0[((size_t)b * a.F + (M - k)) * T + t];
             yk = make_float2(yk.x * ak.x, yk.x * ak.y);
             ymk = make_float2(ymk.x * amk.x, ymk.x * amk.y);
+          } else if (a.seed) {
+            const unsigned long long base = ((unsigned long long)b * T + t) * (M + 1);
+            const float2 ak = rand_angle(a.seed, base + k), amk = rand_angle(a.seed, base + (M - k));
+            yk = make_float2(yk.x * ak.x, yk.x * ak.y);
+            ymk = make_float2(ymk.x * amk.x, ymk.x * amk.y);
           }
           if (k == 0) { yk.y = 0.f; ymk.y = 0.f; }
           irfft_merge(yk, ymk, a.rtw[k], z1, z2);
@@ -205,6 +211,8 @@ __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict_
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
                       int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast.cu
 int gl_fast_warps_per_sm();
+int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
+                           cudaStream_t st);
 
 GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   GlPartition q;
@@ -245,8 +253,8 @@ size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   return bytes;
 }
 
-int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, int B, int T, int n_iter, float momentum,
-           const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st) {
+int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, unsigned long long seed, int B, int T, int n_iter,
+           float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st) {
   B2D_REQUIRE(p->hop * 2 == p->n_fft, B2D_ERR_UNSUPPORTED, "Griffin-Lim requires hop == n_fft/2 (got n_fft=%d hop=%d)", p->n_fft, p->hop);
   B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
   B2D_REQUIRE(momentum >= 0.f && momentum < 1.f, B2D_ERR_BAD_ARG, "momentum must be in range [0, 1). Found: %g", (double)momentum);
@@ -270,9 +278,14 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, in
   B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(q.R, B);
   // x_0 = istft(mag * angles_0)
-  a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa;
-  gl_generic_kernel<<<grid, 256, smem, st>>>(a);
-  B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
+  a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed;
+  if (q.fast && init_angles == nullptr) {
+    int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, st);
+    if (rc != B2D_OK) return rc;
+  } else {
+    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+    B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
+  }
   float* cur = xa;
   float* nxt = xb;
   a.init = 0; a.angles0 = nullptr;

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._runtime import Workspace, get_plan, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
+from ._runtime import Workspace, draw_seed, get_plan, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
 from .gruunet2 import CONV_MODES, GRUUNet2
 
 
@@ -64,8 +64,7 @@ class DenoisePipeline:
         F = self.plan.n_freqs
         dev = x.device
         h = self._hx(hx, B, dev)
-        if init_angles is None and rand_init:
-            init_angles = torch.rand((B, F, T), dtype=torch.complex64, device=dev)  # TA functional.py:310
+        seed = draw_seed() if (init_angles is None and rand_init) else 0  # TA functional.py:310, drawn in-kernel
         if init_angles is not None:
             init_angles = require_cuda_c64(init_angles, "init_angles").reshape(B, F, T)
         wave = out if out is not None else torch.empty((B, self.plan.out_length(T)), dtype=torch.float32, device=dev)
@@ -79,7 +78,7 @@ class DenoisePipeline:
         ws = self._ws.get(lib.b2d_denoise_workspace_bytes(self.plan.handle, handle, B, L), dev)
         with torch.cuda.device(dev):
             _cabi.check(lib.b2d_denoise_batch(
-                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), self.n_iter, float(self.momentum),
+                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
                 1 if normalise else 0, CONV_MODES[self.model.conv_mode], wave.data_ptr(), ptr(logmel), ptr(pred), ptr(mag),
                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         if return_intermediates:
@@ -192,19 +191,17 @@ class StreamingDenoiser:
         self._chunk_host.numpy()[...] = window
         self._chunk_dev.copy_(self._chunk_host, non_blocking=True)
         F = self.plan.n_freqs
-        init = None
+        init, seed = None, 0
         if self.angles_fn is not None:
-            init = self.angles_fn(self.hops, (self.S, F, 3))
-        elif self.n_iter >= 0:
-            init = torch.rand((self.S, F, 3), dtype=torch.complex64, device=dev)
-        if init is not None:
-            init = require_cuda_c64(init.to(dev), "init_angles")
+            init = require_cuda_c64(self.angles_fn(self.hops, (self.S, F, 3)).to(dev), "init_angles")
+        else:
+            seed = draw_seed()
         lib = _cabi.lib()
         handle = self.model.native_handle(dev)
         ws = self._ws.get(lib.b2d_stream_step_workspace_bytes(self.plan.handle, handle, self.S), dev)
         with torch.cuda.device(dev):
             _cabi.check(lib.b2d_stream_step(
-                self.plan.handle, handle, self._chunk_dev.data_ptr(), self.S, self.hx.data_ptr(), self.ola.data_ptr(), ptr(init),
+                self.plan.handle, handle, self._chunk_dev.data_ptr(), self.S, self.hx.data_ptr(), self.ola.data_ptr(), ptr(init), seed,
                 self.n_iter, float(self.momentum), CONV_MODES[self.model.conv_mode], self._out_dev.data_ptr(),
                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         self._out_host.copy_(self._out_dev, non_blocking=True)

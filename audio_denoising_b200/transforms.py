@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from ._runtime import Workspace, get_plan, is_hann, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
+from ._runtime import Workspace, draw_seed, get_plan, is_hann, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
 
 __all__ = ["Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram"]
 
@@ -166,8 +166,11 @@ class GriffinLim(nn.Module):
         B, F, T = s.shape
         if F != self.n_fft // 2 + 1:
             raise ValueError(f"Expected {self.n_fft // 2 + 1} frequency bins. Found: {F}")
+        seed = 0
         if init_angles is None and self.rand_init:
-            init_angles = torch.rand(s.size(), dtype=torch.complex64, device=s.device)
+            # rand_init=True (TA:functional/functional.py:310): U[0,1) real/imag parts drawn inside the kernel from a
+            # counter-based generator seeded from torch's CPU generator (so torch.manual_seed makes runs repeatable)
+            seed = draw_seed()
         if init_angles is not None:
             init_angles = require_cuda_c64(init_angles, "init_angles").reshape(s.shape)
         plan = get_plan(self.n_fft, self.hop_length, 0, 0, s.device)
@@ -176,7 +179,7 @@ class GriffinLim(nn.Module):
         ws = self._ws.get(nbytes, s.device)
         wave = torch.empty((B, plan.out_length(T)), dtype=torch.float32, device=s.device)
         with torch.cuda.device(s.device):
-            _cabi.check(lib.b2d_griffinlim(plan.handle, s.data_ptr(), ptr(init_angles), B, T, self.n_iter, float(self.momentum),
+            _cabi.check(lib.b2d_griffinlim(plan.handle, s.data_ptr(), ptr(init_angles), seed, B, T, self.n_iter, float(self.momentum),
                                            None, wave.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(s.device)))
         return wave.reshape(lead + wave.shape[-1:])
 

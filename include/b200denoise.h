@@ -126,15 +126,16 @@ int b2d_inverse_mel_frames(const b2d_plan* plan, const float* mel_bt, int B, int
 /* ---- K6: GriffinLim(power=1) (app3.py:213; TA:functional/functional.py:255-353) -----------------
  * mag [B, F, T] torch layout (b2d_griffinlim) or [B, T, Fp] frame layout (b2d_griffinlim_frames);
  * init_angles [B, F, T] complex torch layout = the `angles` tensor of TA functional.py:309-312
- * (NULL = rand_init=False, all ones);  momentum is the user-facing value (0.99), rescaled inside as
+ * (when NULL: seed != 0 -> rand_init=True with in-kernel counter-based U[0,1) draws for real and imaginary parts,
+ * seed == 0 -> rand_init=False, all ones);  momentum is the user-facing value (0.99), rescaled inside as
  * at TA functional.py:300;  out_scale (nullable, [B]) multiplies clip b's waveform (app3.py:217).
  * wave [B, hop*(T-1)].  T >= 3. */
 size_t b2d_griffinlim_workspace_bytes(const b2d_plan* plan, int B, int T);
-int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, int B, int T,
-                   int n_iter, float momentum, const float* out_scale, float* wave,
+int b2d_griffinlim(const b2d_plan* plan, const float* mag, const b2d_c64* init_angles, unsigned long long seed,
+                   int B, int T, int n_iter, float momentum, const float* out_scale, float* wave,
                    void* workspace, size_t workspace_bytes, void* stream);
-int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, int B, int T,
-                          int n_iter, float momentum, const float* out_scale, float* wave,
+int b2d_griffinlim_frames(const b2d_plan* plan, const float* mag_tf, const b2d_c64* init_angles, unsigned long long seed,
+                          int B, int T, int n_iter, float momentum, const float* out_scale, float* wave,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K7: InverseSpectrogram / torch.istft (server.py:216; TA:functional/functional.py:205) ------
@@ -148,8 +149,8 @@ int b2d_istft(const b2d_plan* plan, const b2d_c64* spec, const float* mag, int B
  * Optional debug outputs (nullable): logmel_bt, pred_bt [B,T,n_mels], mag_tf [B,T,Fp]. */
 size_t b2d_denoise_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L);
 int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L,
-                      float* hx, const b2d_c64* init_angles, int n_iter, float momentum, int normalise,
-                      int conv_mode, float* wave, float* logmel_bt, float* pred_bt, float* mag_tf,
+                      float* hx, const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum,
+                      int normalise, int conv_mode, float* wave, float* logmel_bt, float* pred_bt, float* mag_tf,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- server.py:207-216 chain (noisy-phase iSTFT, no Griffin-Lim) --------------------------------
@@ -162,11 +163,11 @@ int b2d_denoise_noisy_phase(const b2d_plan* plan, const b2d_model* model, const 
 /* ---- streaming hop, app3.py:178-226 (one `while` iteration for S independent sessions) ----------
  * chunk [S, n_fft] raw float samples (the current input window), hx [S, hidden, bins] in/out,
  * ola [S, n_fft] in/out output overlap-add ring, out [S, hop] the hop of audio emitted by this step.
- * init_angles [S, F, 3] or NULL.  compat != 0 keeps quirks Q2-Q4 of SURVEY.md Appendix C. */
+ * init_angles [S, F, 3] or NULL (then seed as for b2d_griffinlim).  compat != 0 keeps quirks Q2-Q4 of SURVEY.md Appendix C. */
 size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int S);
 int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx,
-                    float* ola, const b2d_c64* init_angles, int n_iter, float momentum, int conv_mode,
-                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+                    float* ola, const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum,
+                    int conv_mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library has launched from the calling process (all threads); bench.py
  * reports the difference across the timed region as "gpu_launches". */
