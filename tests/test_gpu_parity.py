@@ -393,7 +393,7 @@ def test_fast_1024_kernels_match_generic_kernels(dev, monkeypatch):
     assert metrics.si_sdr(fast["gl0"], slow["gl0"]).min() > 110.0  # same random initial phase from the same seed
     assert metrics.si_sdr(fast["gl32"], slow["gl32"]).min() > 60.0
     assert metrics.si_sdr(fast["ones"], slow["ones"]).min() > 90.0
-    assert metrics.si_sdr(fast["ones"], dsp.griffinlim(dsp.stft(x, n_fft, hop).abs(), n_fft, hop, 8, 0.99, None, rand_init=False)).min() > 90.0
+    assert metrics.si_sdr(fast["ones"], dsp.griffinlim(dsp.stft(x, n_fft, hop).abs(), n_fft, hop, 8, 0.99, None, rand_init=False)).min() > 80.0
     # a different seed gives a different (but equally consistent) reconstruction
     monkeypatch.delenv("B2D_GL_GENERIC")
     other = gl(78, 32)
