@@ -26,7 +26,8 @@ int fail(int code, const char* fmt, ...) {
 
 int model_pack(b2d_model* m, const float* const* hp, const float* const* offs);  // model.cu
 bool model_config_supported(const b2d_model_config* c);
-int model_pack_tc(b2d_model* m);  // conv_tc.cu
+int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv);  // conv_tc.cu
+int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);
 int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
                      const float2* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
                      void* ws, size_t ws_bytes, cudaStream_t st);  // stream.cu
@@ -129,6 +130,10 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
     b2d_plan_destroy(p);
     return rc;
   }
+  if ((rc = plan_pack_invmel_tc(p, h_pinv))) {
+    b2d_plan_destroy(p);
+    return rc;
+  }
   *out = p;
   return B2D_OK;
 }
@@ -161,7 +166,6 @@ int b2d_model_create(const b2d_model_config* cfg, const float* const* h_params, 
   m->n_mels = cfg->num_compressed_bins << cfg->levels;
   B2D_CUDA(cudaGetDevice(&m->device));
   int rc = model_pack(m, h_params, h_gs_offsets);
-  if (rc == B2D_OK) rc = model_pack_tc(m);
   if (rc != B2D_OK) {
     b2d_model_destroy(m);
     return rc;
@@ -344,7 +348,11 @@ int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float*
   if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
   if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
-  if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) return rc;
+  if (conv_mode != 0 && plan->d_tw8 != nullptr) {
+    if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, conv_mode == 1 ? 3 : 1, st))) return rc;
+  } else if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) {
+    return rc;
+  }
   return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum,
                 normalise ? w.peak : nullptr, wave, w.gl_ws, w.gl_bytes, st);
 }

@@ -68,7 +68,7 @@ struct b2d_plan {
   float* d_mel_w;     // compact column weights
   int mel_nnz;
   float* d_pinv;      // [Fp, n_mels] rows F..Fp-1 zero
-  float2* d_tw8;      // fast path tables (see gl_fast.cuh), may be null
+  float2* d_tw8;      // TF32 big/small weight images of pinv for the tcgen05 inverse-mel GEMM (conv_tc.cu), may be null
 };
 
 struct b2d_model {

@@ -1,22 +1,487 @@
-// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM variants of the GRUUNet2 encoder / decoder convolutions.
-// (placeholder until the tensor-core path lands: conv_mode 1/2 report B2D_ERR_UNSUPPORTED)
+// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM kernels for the dense contractions of the path:
+// the GRUUNet2 encoder / decoder convolutions (gruunet2.py:71-96) and the inverse-mel projection
+// relu(pinv(fb^T) @ mel) (TA:transforms/_transforms.py:508).
+//
+// One GEMM shape for all of them:  D[128 rows, N] += A[128 rows, K] * B[N, K]^T  with
+//   rows  = (frame, output position) pairs (im2col rows gathered on the fly) or frames (inverse mel),
+//   N     = output channels padded to a multiple of 16, K = (input channel, tap) pairs padded to 8.
+// Operands are fp32 values consumed as TF32 (kind::tf32, K = 8 per instruction) from shared memory in the
+// canonical K-major no-swizzle core-matrix layout; accumulators live in TMEM and come back with
+// tcgen05.ld (one TMEM lane = one output row per thread).  conv_mode 1 ("tf32x3") splits every operand
+// into big + small TF32 parts and issues three MMAs per k-step (big*big + small*big + big*small): the
+// result is fp32-class (~1e-6) although the tensor cores only multiply 11-bit mantissas.  conv_mode 2
+// ("tf32") issues the big*big term only.  The weight images (already split and laid out) are produced at
+// model-pack time and arrive with one TMA bulk copy per CTA.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace b2d {
 
-int model_pack_tc(b2d_model* m) {
-  m->d_tc = nullptr;
-  m->tc_bytes = 0;
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src),
+               "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(s_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- canonical K-major no-swizzle layout (TF32: 4 elements per 16-byte core-matrix row) ---------------
+// element (row, k) of a [rows, KP] operand: ((row/8) * (KP/4) + k/4) * 128 + (row%8) * 16 + (k%4) * 4   [bytes]
+__host__ __device__ inline int canon_off_f(int row, int k, int KP) { return (((row >> 3) * (KP >> 2) + (k >> 2)) << 5) + ((row & 7) << 2) + (k & 3); }  // in floats
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int KP) {
+  const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((KP >> 2) * 128) >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46);  // version 1, SWIZZLE_NONE
+}
+__host__ __device__ inline float tf32_big(float v) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+#else
+  uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r;
+#endif
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24); }
+
+// ---- layer description ------------------------------------------------------------------------------
+struct TcLayer {
+  const float* src0;   // [NF][c0][lin]
+  const float* src1;   // [NF][c1][lin] or null (decoder skip)
+  int c0, c1, lin, lout, cout, transposed, relu, cop;
+  const float* pb;     // [lout][cop] position bias (bias + folded Gaussian channels)
+  const float* wimg;   // device weight image: big [NP*KP] then small [NP*KP], canonical layout
+  float* dst;          // [NF][cout][lout]
+  // last decoder layer: fused residual epilogue
+  const float* x;      // [NF][lout] log-mel input
+  float* mel;          // [NF][lout] or null
+  int fused_mode;
+  float out_scale;
+  size_t nframes;
+  int terms;           // 3 = tf32x3, 1 = tf32
+};
+
+template <int NP, int KP>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const TcLayer L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* A_big = reinterpret_cast<float*>(smem_raw);
+  float* A_small = A_big + 128 * KP;
+  float* B_big = A_small + 128 * KP;
+  float* B_small = B_big + NP * KP;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(B_small + NP * KP);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t TM_COLS = NP <= 32 ? 32 : (NP <= 64 ? 64 : (NP <= 128 ? 128 : 256));
+  if (tid == 0) {
+    tc_mbar_init(bar_w, 1);
+    tc_mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {  // TMA: the pre-laid-out weight image (big | small) in one bulk copy
+    constexpr uint32_t wbytes = 2u * NP * KP * 4u;
+    tc_mbar_expect_tx(bar_w, wbytes);
+    tc_bulk_g2s(B_big, L.wimg, wbytes, bar_w);
+  }
+  const int fpt = 128 / L.lout;  // frames per 128-row tile
+  const size_t tiles = (L.nframes + fpt - 1) / fpt;
+  const int ctot = L.c0 + L.c1;
+  uint32_t mma_phase = 0;
+  bool weights_ready = false;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // ---- gather this thread's im2col row, split into TF32 big / small parts ------------------------------
+    const int r = tid;
+    const size_t frame = tile * fpt + r / L.lout;
+    const int pos = r % L.lout;
+    const bool live = frame < L.nframes;
+#pragma unroll 2
+    for (int kc = 0; kc < KP / 4; ++kc) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = kc * 4 + e;
+        const int ci = k / 3, tap = k - ci * 3;
+        float val = 0.f;
+        if (live && ci < ctot) {
+          int p;
+          bool ok;
+          if (!L.transposed) {
+            p = 2 * pos - 1 + tap;
+            ok = (p >= 0) && (p < L.lin);
+          } else if ((pos & 1) == 0) {
+            p = pos >> 1;
+            ok = (tap == 1);
+          } else {
+            p = (tap == 2) ? (pos >> 1) : (pos >> 1) + 1;
+            ok = (tap != 1) && (p < L.lin);
+          }
+          if (ok) val = (ci < L.c0) ? L.src0[(frame * L.c0 + ci) * L.lin + p] : L.src1[(frame * L.c1 + (ci - L.c0)) * L.lin + p];
+        }
+        v[e] = val;
+      }
+      const float4 big = make_float4(tf32_big(v[0]), tf32_big(v[1]), tf32_big(v[2]), tf32_big(v[3]));
+      const float4 small = make_float4(tf32_big(v[0] - big.x), tf32_big(v[1] - big.y), tf32_big(v[2] - big.z), tf32_big(v[3] - big.w));
+      const int off = canon_off_f(r, kc * 4, KP);
+      *reinterpret_cast<float4*>(A_big + off) = big;
+      *reinterpret_cast<float4*>(A_small + off) = small;
+    }
+    proxy_fence_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      if (!weights_ready) tc_mbar_wait(bar_w, 0);
+      tc_fence_after();
+      const uint32_t ab = s_u32(A_big), as = s_u32(A_small), bb = s_u32(B_big), bs = s_u32(B_small);
+      constexpr uint32_t idesc = idesc_tf32(NP);
+#pragma unroll 1
+      for (int ks = 0; ks < KP / 8; ++ks) {
+        const uint32_t ko = ks * 256;  // two 128-byte core matrices per K = 8 step
+        umma_tf32(tmem, make_desc(ab + ko, KP), make_desc(bb + ko, KP), idesc, ks > 0);
+        if (L.terms == 3) {
+          umma_tf32(tmem, make_desc(as + ko, KP), make_desc(bb + ko, KP), idesc, 1);
+          umma_tf32(tmem, make_desc(ab + ko, KP), make_desc(bs + ko, KP), idesc, 1);
+        }
+      }
+      umma_commit(bar_mma);  // arrives when every MMA above has completed (implies fence::before_thread_sync)
+    }
+    weights_ready = true;
+    tc_mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: this thread owns TMEM lane tid == output row (frame, pos) -----------------------------
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < NP; c0 += 16) {
+      float acc[16];
+      tmem_ld16(lane_addr + c0, acc);
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int co = c0 + q;
+          if (co < L.cout) {
+            float val = acc[q] + L.pb[pos * L.cop + co];
+            if (L.relu) val = fmaxf(val, 0.f);
+            L.dst[(frame * L.cout + co) * L.lout + pos] = val;
+            if (L.fused_mode) {  // last decoder layer (cout == 1): residual + nonlinearity (app3.py:203-208 / server.py:213-215)
+              const float xv = L.x[frame * L.lout + pos];
+              float m;
+              if (L.fused_mode == 1) {
+                float rr = xv - val;
+                rr = rr > 0.f ? rr : 0.2f * rr;
+                m = fmaxf(expm1f(rr), 0.f);
+              } else {
+                m = expf(xv - fmaxf(val, 0.f) * L.out_scale) - 1.0f;
+              }
+              L.mel[frame * L.lout + pos] = m;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and the A tiles are free again
+    tc_fence_after();
+  }
+  if (!weights_ready && tid == 0) tc_mbar_wait(bar_w, 0);  // never leave with a bulk copy in flight
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_COLS);
+}
+
+// ---- inverse mel: out[frame, f] = relu(sum_m mel[frame, m] * P[f, m]) -------------------------------------
+// rows = frames, K = n_mels (64), N = 176 per CTA column (3 columns cover Fp = 516 padded to 528).
+struct TcInvMel {
+  const float* mel;    // [NF][K]
+  const float* wimg;   // 3 x (big | small) images of [176, 64]
+  float* out;          // [NF][Fp]
+  size_t nframes;
+  int Fp, terms;
+};
+constexpr int IM_N = 176, IM_K = 64;
+
+__global__ void __launch_bounds__(128) invmel_tc_kernel(const TcInvMel L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* A_big = reinterpret_cast<float*>(smem_raw);
+  float* A_small = A_big + 128 * IM_K;
+  float* B_big = A_small + 128 * IM_K;
+  float* B_small = B_big + IM_N * IM_K;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(B_small + IM_N * IM_K);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t TM_COLS = 256;
+  if (tid == 0) {
+    tc_mbar_init(bar_w, 1);
+    tc_mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ncol = blockIdx.y;  // which 176-wide slice of the output
+  if (tid == 0) {
+    constexpr uint32_t wbytes = 2u * IM_N * IM_K * 4u;
+    tc_mbar_expect_tx(bar_w, wbytes);
+    tc_bulk_g2s(B_big, L.wimg + (size_t)ncol * 2 * IM_N * IM_K, wbytes, bar_w);
+  }
+  const size_t tiles = (L.nframes + 127) / 128;
+  uint32_t mma_phase = 0;
+  bool weights_ready = false;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const size_t frame = tile * 128 + tid;
+    const bool live = frame < L.nframes;
+    const float4* src = reinterpret_cast<const float4*>(L.mel + frame * IM_K);
+#pragma unroll 4
+    for (int kc = 0; kc < IM_K / 4; ++kc) {
+      const float4 v = live ? src[kc] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 big = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+      const float4 small = make_float4(tf32_big(v.x - big.x), tf32_big(v.y - big.y), tf32_big(v.z - big.z), tf32_big(v.w - big.w));
+      const int off = canon_off_f(tid, kc * 4, IM_K);
+      *reinterpret_cast<float4*>(A_big + off) = big;
+      *reinterpret_cast<float4*>(A_small + off) = small;
+    }
+    proxy_fence_async();
+    __syncthreads();
+    if (tid == 0) {
+      if (!weights_ready) tc_mbar_wait(bar_w, 0);
+      tc_fence_after();
+      const uint32_t ab = s_u32(A_big), as = s_u32(A_small), bb = s_u32(B_big), bs = s_u32(B_small);
+      constexpr uint32_t idesc = idesc_tf32(IM_N);
+#pragma unroll 1
+      for (int ks = 0; ks < IM_K / 8; ++ks) {
+        const uint32_t ko = ks * 256;
+        umma_tf32(tmem, make_desc(ab + ko, IM_K), make_desc(bb + ko, IM_K), idesc, ks > 0);
+        if (L.terms == 3) {
+          umma_tf32(tmem, make_desc(as + ko, IM_K), make_desc(bb + ko, IM_K), idesc, 1);
+          umma_tf32(tmem, make_desc(ab + ko, IM_K), make_desc(bs + ko, IM_K), idesc, 1);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    weights_ready = true;
+    tc_mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    float* orow = L.out + frame * L.Fp + (size_t)ncol * IM_N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < IM_N; c0 += 16) {
+      float acc[16];
+      tmem_ld16(lane_addr + c0, acc);
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          if (ncol * IM_N + c0 + q < L.Fp)  // Fp is a multiple of 4: whole float4 groups are in or out
+            *reinterpret_cast<float4*>(orow + c0 + q) =
+                make_float4(fmaxf(acc[q], 0.f), fmaxf(acc[q + 1], 0.f), fmaxf(acc[q + 2], 0.f), fmaxf(acc[q + 3], 0.f));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (!weights_ready && tid == 0) tc_mbar_wait(bar_w, 0);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+// model: 9 weight images.  layer order: enc0..3, dec0..3 ; shapes (NP, KP):
+static const int kNP[8] = {32, 32, 32, 64, 32, 32, 32, 16};
+static const int kKP[8] = {8, 56, 56, 56, 56, 104, 104, 104};
+
+static void put_image(std::vector<float>& img, size_t base, int NP, int KP, int n, int k, float w) {
+  const float big = tf32_big(w);
+  img[base + canon_off_f(n, k, KP)] = big;
+  img[base + (size_t)NP * KP + canon_off_f(n, k, KP)] = tf32_big(w - big);
+}
+
+int model_pack_tc_weights(b2d_model* m, const float* const* hp) {
+  const int H = m->cfg.hidden, G = m->cfg.num_gaussians, LV = m->cfg.levels;
+  size_t total = 0;
+  for (int l = 0; l < 2 * LV; ++l) {
+    m->tc_off[l] = (int)total;
+    total += 2 * (size_t)kNP[l] * kKP[l];
+  }
+  std::vector<float> img(total, 0.f);
+  for (int l = 0; l < LV; ++l) {  // encoder: Conv1d weight [co][ci+G][3]
+    const int cin = l == 0 ? 1 : H, cout = (l == LV - 1) ? 3 * H : H, CT = cin + G;
+    const float* W = hp[2 * l];
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < 3; ++t) put_image(img, m->tc_off[l], kNP[l], kKP[l], co, ci * 3 + t, W[(co * CT + ci) * 3 + t]);
+  }
+  for (int i = 0; i < LV; ++i) {  // decoder: ConvTranspose1d weight [ci+G][co][3]
+    const int cin = i == 0 ? H : 2 * H, cout = (i == LV - 1) ? 1 : H;
+    const float* W = hp[2 * LV + 2 + 2 * i];
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < 3; ++t) put_image(img, m->tc_off[LV + i], kNP[LV + i], kKP[LV + i], co, ci * 3 + t, W[(ci * cout + co) * 3 + t]);
+  }
+  m->tc_bytes = total * sizeof(float);
+  B2D_CUDA(cudaMalloc(&m->d_tc, m->tc_bytes));
+  B2D_CUDA(cudaMemcpy(m->d_tc, img.data(), m->tc_bytes, cudaMemcpyHostToDevice));
   return B2D_OK;
 }
 
-int model_forward_tc(const b2d_model*, const float*, size_t, float*, float*, float*, float*, int, cudaStream_t) {
-  return fail(B2D_ERR_UNSUPPORTED, "tcgen05 encoder path not built into this library yet (use conv_mode=0)");
+int model_pack_tc(b2d_model* m) { (void)m; return B2D_OK; }  // weights are packed by model_pack_tc_weights (needs the host tensors)
+
+template <int NP, int KP>
+static int launch_layer(const TcLayer& L, int num_sms, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)(2 * 128 * KP + 2 * NP * KP) + 64;
+  B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NP, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int fpt = 128 / L.lout;
+  const size_t tiles = (L.nframes + fpt - 1) / fpt;
+  const size_t cap = (size_t)num_sms * (smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3));
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  conv_tc_kernel<NP, KP><<<grid, 128, smem, st>>>(L);
+  B2D_LAUNCH_CHECK("conv_tc_kernel");
+  return B2D_OK;
 }
 
-int model_decode_tc(const b2d_model*, const float*, const float*, const float*, const float*, const float*, size_t, float*,
-                    float*, int, float, int, cudaStream_t) {
-  return fail(B2D_ERR_UNSUPPORTED, "tcgen05 decoder path not built into this library yet (use conv_mode=0)");
+// blob layout offsets of the fp32 path (model.cu): position biases are shared
+struct PackedOffsets { int enc_pb[4]; int dec_pb[4]; };
+PackedOffsets packed_offsets();  // model.cu
+
+int model_forward_tc(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx,
+                     int conv_mode, cudaStream_t st) {
+  B2D_REQUIRE(m->d_tc != nullptr, B2D_ERR_UNSUPPORTED, "tensor-core weight images were not packed for this model");
+  const PackedOffsets po = packed_offsets();
+  const int H = m->cfg.hidden;
+  const float* wt = static_cast<const float*>(m->d_tc);
+  TcLayer L{};
+  L.nframes = nframes; L.terms = conv_mode == 1 ? 3 : 1; L.transposed = 0; L.relu = 1; L.src1 = nullptr; L.c1 = 0;
+  L.fused_mode = 0; L.x = nullptr; L.mel = nullptr; L.out_scale = 0.f;
+  int rc;
+  const int num_sms = 148;
+  // enc0: [1][64] -> [17][32]
+  L.src0 = x; L.c0 = 1; L.lin = 64; L.lout = 32; L.cout = H; L.cop = 20; L.pb = m->d_blob + po.enc_pb[0]; L.wimg = wt + m->tc_off[0]; L.dst = d0;
+  if ((rc = launch_layer<32, 8>(L, num_sms, st))) return rc;
+  L.src0 = d0; L.c0 = H; L.lin = 32; L.lout = 16; L.pb = m->d_blob + po.enc_pb[1]; L.wimg = wt + m->tc_off[1]; L.dst = d1;
+  if ((rc = launch_layer<32, 56>(L, num_sms, st))) return rc;
+  L.src0 = d1; L.lin = 16; L.lout = 8; L.pb = m->d_blob + po.enc_pb[2]; L.wimg = wt + m->tc_off[2]; L.dst = d2;
+  if ((rc = launch_layer<32, 56>(L, num_sms, st))) return rc;
+  L.src0 = d2; L.lin = 8; L.lout = 4; L.cout = 3 * H; L.cop = 52; L.pb = m->d_blob + po.enc_pb[3]; L.wimg = wt + m->tc_off[3]; L.dst = gx;
+  return launch_layer<64, 56>(L, num_sms, st);
+}
+
+int model_decode_tc(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
+                    size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int conv_mode, float* scratch,
+                    cudaStream_t st) {
+  B2D_REQUIRE(m->d_tc != nullptr, B2D_ERR_UNSUPPORTED, "tensor-core weight images were not packed for this model");
+  const PackedOffsets po = packed_offsets();
+  const int H = m->cfg.hidden;
+  const float* wt = static_cast<const float*>(m->d_tc);
+  // scratch: u0 [NF][17][8] | u1 [NF][17][16] | u2 [NF][17][32]
+  float* u0 = scratch;
+  float* u1 = u0 + nframes * H * 8;
+  float* u2 = u1 + nframes * H * 16;
+  TcLayer L{};
+  L.nframes = nframes; L.terms = conv_mode == 1 ? 3 : 1; L.transposed = 1; L.relu = 1; L.cop = 20; L.cout = H;
+  L.fused_mode = 0; L.x = nullptr; L.mel = nullptr; L.out_scale = out_scale;
+  int rc;
+  const int num_sms = 148;
+  L.src0 = hseq; L.c0 = H; L.src1 = nullptr; L.c1 = 0; L.lin = 4; L.lout = 8; L.pb = m->d_blob + po.dec_pb[0]; L.wimg = wt + m->tc_off[4]; L.dst = u0;
+  if ((rc = launch_layer<32, 56>(L, num_sms, st))) return rc;
+  L.src0 = u0; L.src1 = d2; L.c1 = H; L.lin = 8; L.lout = 16; L.pb = m->d_blob + po.dec_pb[1]; L.wimg = wt + m->tc_off[5]; L.dst = u1;
+  if ((rc = launch_layer<32, 104>(L, num_sms, st))) return rc;
+  L.src0 = u1; L.src1 = d1; L.lin = 16; L.lout = 32; L.pb = m->d_blob + po.dec_pb[2]; L.wimg = wt + m->tc_off[6]; L.dst = u2;
+  if ((rc = launch_layer<32, 104>(L, num_sms, st))) return rc;
+  L.src0 = u2; L.src1 = d0; L.lin = 32; L.lout = 64; L.cout = 1; L.cop = 4; L.relu = 0; L.pb = m->d_blob + po.dec_pb[3]; L.wimg = wt + m->tc_off[7];
+  L.dst = pred; L.fused_mode = fused_mode; L.x = x; L.mel = mel;
+  return launch_layer<16, 104>(L, num_sms, st);
+}
+
+// plan: inverse-mel weight images (3 column slices of [176, 64], big | small each)
+int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv) {
+  if (p->n_mels != IM_K || p->Fp > 3 * IM_N) { p->d_tw8 = nullptr; return B2D_OK; }  // only the 64-mel, n_fft <= 1048 shape
+  std::vector<float> img((size_t)3 * 2 * IM_N * IM_K, 0.f);
+  for (int f = 0; f < p->F; ++f) {
+    const int col = f / IM_N, n = f - col * IM_N;
+    for (int k = 0; k < IM_K; ++k) put_image(img, (size_t)col * 2 * IM_N * IM_K, IM_N, IM_K, n, k, h_pinv[(size_t)f * IM_K + k]);
+  }
+  float* d = nullptr;
+  B2D_CUDA(cudaMalloc(&d, img.size() * sizeof(float)));
+  B2D_CUDA(cudaMemcpy(d, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->d_tw8 = reinterpret_cast<float2*>(d);
+  return B2D_OK;
+}
+
+int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st) {
+  B2D_REQUIRE(p->d_tw8 != nullptr, B2D_ERR_UNSUPPORTED, "tensor-core inverse mel needs n_mels == 64 and n_fft <= 1048");
+  TcInvMel L;
+  L.mel = mel_bt; L.wimg = reinterpret_cast<const float*>(p->d_tw8); L.out = mag_tf; L.nframes = nframes; L.Fp = p->Fp; L.terms = terms;
+  const size_t smem = sizeof(float) * (size_t)(2 * 128 * IM_K + 2 * IM_N * IM_K) + 64;
+  B2D_CUDA(cudaFuncSetAttribute(invmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t tiles = (nframes + 127) / 128;
+  const int ncols = (p->Fp + IM_N - 1) / IM_N;
+  const size_t cap = (size_t)(p->num_sms / ncols > 0 ? p->num_sms / ncols : 1);
+  dim3 grid((unsigned)(tiles < cap ? tiles : cap), ncols);
+  invmel_tc_kernel<<<grid, 128, smem, st>>>(L);
+  B2D_LAUNCH_CHECK("invmel_tc_kernel");
+  return B2D_OK;
 }
 
 }  // namespace b2d

@@ -343,6 +343,8 @@ static void smear_table(const float* off, int G, int nbins, std::vector<double>&
   }
 }
 
+int model_pack_tc_weights(b2d_model* m, const float* const* hp);  // conv_tc.cu
+
 int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
   const Packed L = packed_layout();
   const int G = m->cfg.num_gaussians;
@@ -426,7 +428,15 @@ int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
   m->blob_floats = blob.size();
   B2D_CUDA(cudaMalloc(&m->d_blob, blob.size() * sizeof(float)));
   B2D_CUDA(cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
-  return B2D_OK;
+  return model_pack_tc_weights(m, hp);  // TF32 big/small weight images for the tcgen05 path (conv_tc.cu)
+}
+
+struct PackedOffsets { int enc_pb[4]; int dec_pb[4]; };
+PackedOffsets packed_offsets() {
+  const Packed L = packed_layout();
+  PackedOffsets o;
+  for (int i = 0; i < 4; ++i) { o.enc_pb[i] = L.enc_pb[i]; o.dec_pb[i] = L.dec_pb[i]; }
+  return o;
 }
 
 bool model_config_supported(const b2d_model_config* c) {
@@ -434,18 +444,19 @@ bool model_config_supported(const b2d_model_config* c) {
          c->padding == 1 && c->num_gaussians >= 2 && c->num_gaussians <= 16;
 }
 
-// workspace: d0 | d1 | d2 | gx | hseq   (per frame: D0+D1+D2+GX+HS floats)
+// workspace: d0 | d1 | d2 | gx | hseq | decoder scratch u0,u1,u2 (tensor-core path)
 size_t model_workspace_bytes(const b2d_model* m, int B, int T) {
   (void)m;
   const size_t nf = (size_t)B * T;
   return align_up(nf * D0 * 4, 256) + align_up(nf * D1 * 4, 256) + align_up(nf * D2 * 4, 256) + align_up(nf * GX * 4, 256) +
-         align_up(nf * HS * 4, 256);
+         align_up(nf * HS * 4, 256) + align_up(nf * (size_t)H * (8 + 16 + 32) * 4, 256);
 }
 
 int model_forward_tc(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx,
                      int conv_mode, cudaStream_t st);  // conv_tc.cu
 int model_decode_tc(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
-                    size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int conv_mode, cudaStream_t st);
+                    size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int conv_mode, float* scratch,
+                    cudaStream_t st);
 
 int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, float* mel_bt, int fused_mode,
                   float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -458,7 +469,8 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   float* d1 = reinterpret_cast<float*>(base); base += align_up(nf * D1 * 4, 256);
   float* d2 = reinterpret_cast<float*>(base); base += align_up(nf * D2 * 4, 256);
   float* gx = reinterpret_cast<float*>(base); base += align_up(nf * GX * 4, 256);
-  float* hseq = reinterpret_cast<float*>(base);
+  float* hseq = reinterpret_cast<float*>(base); base += align_up(nf * HS * 4, 256);
+  float* dec_scratch = reinterpret_cast<float*>(base);
   const Packed L = packed_layout();
   int dev_sms = 148;
   if (conv_mode == 0) {
@@ -483,7 +495,7 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
     decoder_kernel<<<grid, DEC_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
     B2D_LAUNCH_CHECK("decoder_kernel");
   } else {
-    int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, st);
+    int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, dec_scratch, st);
     if (rc != B2D_OK) return rc;
   }
   return B2D_OK;

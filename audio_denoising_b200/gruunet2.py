@@ -24,7 +24,9 @@ from torch import nn
 from . import _cabi
 from ._runtime import Workspace, require_cuda_f32, stream_ptr
 
-CONV_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+# "fp32": CUDA-core FMA convolutions; "tf32x3": tcgen05 implicit GEMM, operands split into big+small TF32 parts (3 MMAs,
+# fp32-class accuracy); "tf32": tcgen05 single pass (11-bit mantissa operands, fp32 accumulate)
+CONV_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
 
 
 class _PositionCode(nn.Module):
@@ -84,7 +86,7 @@ class GRUUNet2(nn.Module):
         self.latent_size = hidden_sizes[-1]
         self.num_compressed_bins = num_compressed_bins
         self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
-        self.conv_mode = "fp32"  # "fp32" (CUDA cores, parity) | "bf16x3" | "bf16" (tcgen05 implicit GEMM)
+        self.conv_mode = "fp32"  # one of CONV_MODES
         self._native = None  # (signature, handle, finalizer)
         self._ws = Workspace()
 

@@ -105,8 +105,9 @@ int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* m
 /* ---- K3: GRUUNet2.forward (gruunet2.py:290-306) -----------------------------------------------
  * x [B, T, n_mels], hx [B, hidden, bins] in/out (caller zero-fills it for hx=None), out [B, T, n_mels].
  * Runs encoder (time-parallel) -> persistent recurrence -> decoder (time-parallel).
- * conv_mode: 0 = fp32 CUDA-core convolutions (parity mode), 1 = tcgen05 bf16x3 split (tensor cores,
- * fp32-class accuracy), 2 = tcgen05 plain bf16 (throughput mode). */
+ * conv_mode: 0 = fp32 CUDA-core convolutions, 1 = tcgen05/TMEM implicit GEMM with TF32 operands split into
+ * big + small parts (3 MMAs per k-step, fp32-class accuracy), 2 = tcgen05 single-pass TF32 (throughput mode).
+ * In the fused chains conv_mode != 0 also runs the inverse-mel projection as a tcgen05 GEMM. */
 size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T);
 int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T,
                          int conv_mode, void* workspace, size_t workspace_bytes, void* stream);

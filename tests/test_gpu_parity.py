@@ -422,3 +422,52 @@ def test_rand_init_draws_are_uniform(dev):
     assert 0.0 <= float(centres.min()) and float(centres.max()) < 1.0
     assert abs(float(centres.mean()) - 0.5) < 0.08
     assert float(centres.std()) > 0.2
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 path
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+def test_model_tensor_core_modes(dev, golden, mode, tol):
+    """conv_mode tf32x3 / tf32: encoder + decoder as tcgen05/TMEM implicit GEMMs (conv_tc.cu)."""
+    _, metrics, model, *_ = _oracle()
+    z = golden("model_io.npz")
+    x = torch.from_numpy(z["x"]).to(dev)
+    for name in CHECKPOINTS:
+        m, sd, cfg = _our_model(name, dev)
+        m.conv_mode = mode
+        y, h = m(x)
+        assert metrics.rel_l2(y.cpu(), torch.from_numpy(z[f"{name}_y"])) < tol, name
+        assert metrics.rel_l2(h.cpu(), torch.from_numpy(z[f"{name}_h"])) < tol, name
+    # a batch that is not a multiple of the 128-row tiles, long sequence
+    sd = model.random_state_dict(seed=5)
+    import audio_denoising_b200 as adb
+
+    m = adb.GRUUNet2(**model.default_config())
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    m.conv_mode = mode
+    g = torch.Generator().manual_seed(11)
+    xx = torch.rand(3, 37, 64, generator=g) * 3
+    ry, rh = model.GRUUNet2Oracle(sd)(xx)
+    y, h = m(xx.to(dev))
+    assert metrics.rel_l2(y.cpu(), ry) < tol and metrics.rel_l2(h.cpu(), rh) < tol
+
+
+def test_pipeline_tensor_core_mode_within_budget(dev):
+    """Whole chain with conv_mode tf32x3 (incl. the tcgen05 inverse-mel GEMM): same 0.05 dB SI-SDR budget."""
+    import audio_denoising_b200 as adb
+
+    dsp, metrics, model, pipeline, synth = _oracle()
+    noisy, clean = synth.make_batch(4, 16000, 16000, start=80)
+    m, sd, cfg = _our_model("good", dev)
+    m.conv_mode = "tf32x3"
+    T = 1 + 16000 // 512
+    init = synth.gl_init_angles((4, 513, T), seed=7)
+    ref = pipeline.denoise_batch(noisy, model.GRUUNet2Oracle(sd, cfg), 1024, 512, 64, 16000, 32, 0.99, init)
+    pipe = adb.DenoisePipeline(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=16000)
+    r = pipe.denoise(noisy.to(dev), init_angles=init.to(dev), return_intermediates=True)
+    assert metrics.rel_l2(r["pred"].cpu(), ref["pred"]) < 1e-5
+    assert metrics.rel_l2(r["lin_mag"].cpu(), ref["lin_mag"]) < 2e-5
+    Lout = r["wave"].shape[1]
+    a = metrics.si_sdr(r["wave"].cpu(), clean[:, :Lout])
+    b = metrics.si_sdr(ref["wave"], clean[:, :Lout])
+    assert (a - b).abs().max() <= 0.05
