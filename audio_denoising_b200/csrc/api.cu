@@ -1,6 +1,7 @@
 // api.cu -- extern "C" surface of libb200denoise.so (declared in include/b200denoise.h).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -248,7 +249,9 @@ int b2d_inverse_mel(const b2d_plan* plan, const float* mel, int B, int T, float*
 int b2d_inverse_mel_frames(const b2d_plan* plan, const float* mel_bt, int B, int T, float* mag_tf, void* stream) {
   B2D_REQUIRE(plan && mel_bt && mag_tf, B2D_ERR_BAD_ARG, "NULL pointer");
   B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "B and T must be >= 1");
-  B2D_REQUIRE(aligned16(mag_tf), B2D_ERR_ALIGN, "mag_tf must be 16-byte aligned");
+  B2D_REQUIRE(aligned16(mag_tf) && aligned16(mel_bt), B2D_ERR_ALIGN, "mel_bt / mag_tf must be 16-byte aligned");
+  if (plan->d_tw8 != nullptr && getenv("B2D_INVMEL_FP32") == nullptr)
+    return launch_inverse_mel_tc(plan, mel_bt, (size_t)B * T, mag_tf, 3, ST(stream));
   return launch_inverse_mel(plan, mel_bt, B, T, mag_tf, false, ST(stream));
 }
 
@@ -348,8 +351,10 @@ int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float*
   if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
   if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
-  if (conv_mode != 0 && plan->d_tw8 != nullptr) {
-    if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, conv_mode == 1 ? 3 : 1, st))) return rc;
+  // inverse mel: tcgen05 GEMM (TF32 big/small split = fp32-class; single pass only in conv_mode 2) when the plan has the
+  // weight images, else the CUDA-core SGEMM
+  if (plan->d_tw8 != nullptr && getenv("B2D_INVMEL_FP32") == nullptr) {
+    if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, conv_mode == 2 ? 1 : 3, st))) return rc;
   } else if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) {
     return rc;
   }

@@ -72,7 +72,7 @@ __device__ __forceinline__ void enc_layer(const float* __restrict__ in, const fl
   for (int item = lane; item < LOUT * NG; item += 32) {
     const int j = item % LOUT, cg = item / LOUT;
     float4 acc = *reinterpret_cast<const float4*>(PB + j * COP + cg * 4);
-#pragma unroll 1
+#pragma unroll 6
     for (int ci = 0; ci < CIN; ++ci) {
       const float* row = in + ci * LIN;
 #pragma unroll
@@ -231,7 +231,7 @@ __device__ __forceinline__ void dec_layer(const float* __restrict__ in, const fl
     const int j = o >> 1;
     const bool odd = o & 1;
     float4 acc = *reinterpret_cast<const float4*>(PB + o * COP + cg * 4);
-#pragma unroll 1
+#pragma unroll 6
     for (int ci = 0; ci < CIN; ++ci) {
       const float* row = in + ci * LIN;
       const float v0 = row[j];

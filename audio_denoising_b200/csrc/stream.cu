@@ -8,6 +8,8 @@
 
 namespace b2d {
 
+int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);  // conv_tc.cu
+
 // workspace: peak[S] | x[S,N] | logmel[S,3,M] | pred | mel | mag[S,3,Fp] | y[S,N] | model ws | GL ws
 struct StreamWs {
   float *peak, *x, *logmel, *pred, *mel, *mag, *y;
@@ -89,7 +91,11 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
   B2D_LAUNCH_CHECK("stream_pre_kernel");
   if ((rc = launch_stft(p, w.x, nullptr, S, N, w.logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(m, w.logmel, hx, w.pred, w.mel, 1, 0.f, S, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
-  if ((rc = launch_inverse_mel(p, w.mel, S, T, w.mag, false, st))) return rc;
+  if (p->d_tw8 != nullptr) {
+    if ((rc = launch_inverse_mel_tc(p, w.mel, (size_t)S * T, w.mag, conv_mode == 2 ? 1 : 3, st))) return rc;
+  } else if ((rc = launch_inverse_mel(p, w.mel, S, T, w.mag, false, st))) {
+    return rc;
+  }
   if ((rc = gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st))) return rc;
   stream_ola_kernel<<<S, 256, 0, st>>>(w.y, ola, out, p->hop);
   B2D_LAUNCH_CHECK("stream_ola_kernel");

@@ -108,12 +108,14 @@ class DenoisePipeline:
 
     # -- host-to-host (end-to-end) ----------------------------------------------------------------
     @torch.no_grad()
-    def denoise_host(self, noisy_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunks: int = 4,
-                     rand_init: bool = True, init_angles: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def denoise_host(self, noisy_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunks: int = 1,
+                     rand_init: bool = True, init_angles: Optional[torch.Tensor] = None, wait: bool = True) -> torch.Tensor:
         """noisy_host [B, L] pinned CPU float32 -> pinned CPU [B, hop*(T-1)].
 
-        The batch is cut into ``chunks`` slices; slice i+1's host->device copy and slice i-1's
-        device->host copy overlap slice i's kernels (three streams, events for ordering).
+        Copies run on their own streams: host->device on ``h2d``, kernels on the current stream, device->host on
+        ``d2h``, ordered by events.  With ``wait=False`` the call only enqueues work, so consecutive batches pipeline
+        (batch i+1's upload and batch i-1's download overlap batch i's kernels); call ``host_synchronize()`` before
+        reading ``out_host``.  ``chunks > 1`` additionally slices one batch so its own copies overlap its own kernels.
         """
         if noisy_host.is_cuda:
             raise ValueError("denoise_host takes host tensors; use denoise() for device tensors")
@@ -129,9 +131,6 @@ class DenoisePipeline:
             self._host = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev))
         h2d, d2h = self._host["h2d"], self._host["d2h"]
         compute = torch.cuda.current_stream(dev)
-        h2d.wait_stream(compute)
-        d2h.wait_stream(compute)
-        keep = []
         for i in range(chunks):
             lo, hi = bounds[i], bounds[i + 1]
             with torch.cuda.stream(h2d):
@@ -148,9 +147,15 @@ class DenoisePipeline:
                 d2h.wait_event(ev_done)
                 out_host[lo:hi].copy_(wave, non_blocking=True)
                 wave.record_stream(d2h)
-            keep.append((xin, wave))
-        compute.wait_stream(d2h)
+        if wait:
+            self.host_synchronize()
         return out_host
+
+    def host_synchronize(self) -> None:
+        """Block until every batch enqueued by ``denoise_host(wait=False)`` has landed in host memory."""
+        if self._host is not None:
+            self._host["d2h"].synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
 
 
 class StreamingDenoiser:
