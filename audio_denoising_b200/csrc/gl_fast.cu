@@ -376,6 +376,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft_fast512_kernel(const StftF
     const float* x = a.wave + (size_t)b * a.L;
     const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
     const long s0 = (long)t * HOP - HOP;  // first sample of the frame in clip coordinates
+    {  // next frame of this warp -> L2 (4 KB = 32 lines)
+      const size_t fn = f + (size_t)gridDim.x * WARPS;
+      if (fn < nframes) {
+        const int bn = (int)(fn / a.T), tn = (int)(fn - (size_t)bn * a.T);
+        const long sn = (long)tn * HOP - HOP + lane * 32;
+        if (sn >= 0 && sn + 32 <= a.L) prefetch_l2(a.wave + (size_t)bn * a.L + sn);
+      }
+    }
     float2 v[16];
     if (even && s0 >= 0 && s0 + N <= a.L) {
       const float2* src = reinterpret_cast<const float2*>(x + s0);

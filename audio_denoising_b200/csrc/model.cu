@@ -10,11 +10,18 @@
 // This file holds the fp32 CUDA-core convolutions (conv_mode 0, the parity mode); conv_tc.cu holds
 // the tcgen05 implicit-GEMM variants of the encoder / decoder.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "kernels.cuh"
 
 namespace b2d {
+
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// warm L2 with [p, p + bytes): one 128-byte line per lane per round
+__device__ __forceinline__ void prefetch_l2_range(const float* p, int bytes, int lane) {
+  for (int o = lane * 128; o < bytes; o += 32 * 128) prefetch_l2_line(reinterpret_cast<const char*>(p) + o);
+}
 
 // shipped configuration (all three checkpoints): hidden 17, 4 levels, 4 compressed bins
 constexpr int H = 17;
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encoder_kernel(const float* __
   float* a3 = a2 + D2;
   for (size_t f = (size_t)blockIdx.x * ENC_WARPS + warp; f < nframes; f += (size_t)gridDim.x * ENC_WARPS) {
     const float* xf = x + f * NMEL;
+    if (lane < 2 && f + (size_t)gridDim.x * ENC_WARPS < nframes) prefetch_l2_line(xf + (size_t)gridDim.x * ENC_WARPS * NMEL + lane * 32);
     a_in[lane] = xf[lane];
     a_in[lane + 32] = xf[lane + 32];
     __syncwarp();
@@ -315,6 +323,150 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decoder_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// decoder, register-tiled: a warp works on FW = 2 frames at once; a lane owns one INPUT position j of one
+// frame and computes all output channels of both outputs 2j and 2j+1 (2 x 17 accumulators in registers).
+// Per input channel: 2 activation loads, 15 broadcast float4 weight loads, 60 FMAs.
+// Per-frame staging (floats): region A [544] = s2 [34][16] (also s0 [17][4] and the final [64]),
+//                             region B [1088] = s3 [34][32] (also s1 [34][8]); skips sit in the upper channel halves.
+// ------------------------------------------------------------------------------------------------
+constexpr int DEC2_WARPS = 6;
+constexpr int DEC2_FW = 2;
+constexpr int DEC2_FR = 544 + 1088 + 16;  // +16: the two frames of a warp land on different banks
+
+template <int CIN, int COUT, int COP, int LIN, bool RELU>
+__device__ __forceinline__ void dec2_layer(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ PB,
+                                           float* __restrict__ out, int j) {
+  constexpr int NG = COP / 4;
+  float4 ae[NG], ao[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    ae[g] = *reinterpret_cast<const float4*>(PB + (2 * j) * COP + 4 * g);
+    ao[g] = *reinterpret_cast<const float4*>(PB + (2 * j + 1) * COP + 4 * g);
+  }
+  const bool has_next = (j + 1 < LIN);
+#pragma unroll 2
+  for (int ci = 0; ci < CIN; ++ci) {
+    const float a0 = in[ci * LIN + j];
+    const float a1 = has_next ? in[ci * LIN + j + 1] : 0.f;
+    const float* w = W + ci * 3 * COP;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * g);
+      const float4 w1 = *reinterpret_cast<const float4*>(w + COP + 4 * g);
+      const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * COP + 4 * g);
+      ae[g].x = fmaf(a0, w1.x, ae[g].x); ae[g].y = fmaf(a0, w1.y, ae[g].y);
+      ae[g].z = fmaf(a0, w1.z, ae[g].z); ae[g].w = fmaf(a0, w1.w, ae[g].w);
+      ao[g].x = fmaf(a0, w2.x, fmaf(a1, w0.x, ao[g].x)); ao[g].y = fmaf(a0, w2.y, fmaf(a1, w0.y, ao[g].y));
+      ao[g].z = fmaf(a0, w2.z, fmaf(a1, w0.z, ao[g].z)); ao[g].w = fmaf(a0, w2.w, fmaf(a1, w0.w, ao[g].w));
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float e[4] = {ae[g].x, ae[g].y, ae[g].z, ae[g].w};
+    const float o[4] = {ao[g].x, ao[g].y, ao[g].z, ao[g].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = 4 * g + q;
+      if (co < COUT) {
+        float2 r = make_float2(e[q], o[q]);
+        if (RELU) r = make_float2(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f));
+        *reinterpret_cast<float2*>(out + co * (2 * LIN) + 2 * j) = r;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DEC2_WARPS * 32, 2) decoder2_kernel(const float* __restrict__ blob, const float* __restrict__ hseq,
+                                                                      const float* __restrict__ d0, const float* __restrict__ d1,
+                                                                      const float* __restrict__ d2, const float* __restrict__ x,
+                                                                      size_t nframes, float* __restrict__ pred, float* __restrict__ mel,
+                                                                      int fused_mode, float out_scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Packed L = packed_layout();
+  float* wts = reinterpret_cast<float*>(smem_raw);
+  const int w0 = L.dec_w[0];
+  const int nw = L.total - w0;
+  float* act = wts + ((nw + 3) & ~3);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[w0 + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = act + warp * (DEC2_FW * DEC2_FR);
+  const size_t stride = (size_t)gridDim.x * DEC2_WARPS * DEC2_FW;
+  for (size_t f0 = ((size_t)blockIdx.x * DEC2_WARPS + warp) * DEC2_FW; f0 < nframes; f0 += stride) {
+    const int nf = (int)min((size_t)DEC2_FW, nframes - f0);
+    if (f0 + stride + DEC2_FW <= nframes) {  // next iteration's inputs -> L2 while this one computes
+      const size_t fn = f0 + stride;
+      prefetch_l2_range(d0 + fn * D0, DEC2_FW * D0 * 4, lane);
+      prefetch_l2_range(d1 + fn * D1, DEC2_FW * D1 * 4, lane);
+      prefetch_l2_range(d2 + fn * D2, DEC2_FW * D2 * 4, lane);
+      prefetch_l2_range(hseq + fn * HS, DEC2_FW * HS * 4, lane);
+      prefetch_l2_range(x + fn * NMEL, DEC2_FW * NMEL * 4, lane);
+    }
+    // stage hidden state and skips of both frames (frames are contiguous in global memory)
+    for (int f = 0; f < nf; ++f) {
+      float* A = base + f * DEC2_FR;  // region A
+      float* Bq = A + 544;            // region B
+      const size_t fr = f0 + f;
+      for (int i = lane; i < HS; i += 32) A[i] = hseq[fr * HS + i];                 // s0 [17][4]
+      for (int i = lane; i < D2; i += 32) Bq[H * 8 + i] = d2[fr * D2 + i];          // s1 upper half
+      for (int i = lane; i < D1; i += 32) A[H * 16 + i] = d1[fr * D1 + i];          // s2 upper half
+      for (int i = lane; i < D0; i += 32) Bq[H * 32 + i] = d0[fr * D0 + i];         // s3 upper half
+    }
+    __syncwarp();
+    {  // up0: [17][4] -> [17][8]   (lanes f*4 + j)
+      const int f = lane >> 2, j = lane & 3;
+      if (lane < 4 * DEC2_FW && f < nf) {
+        float* A = base + f * DEC2_FR;
+        dec2_layer<H, H, HP, 4, true>(A, wts + (L.dec_w[0] - w0), wts + (L.dec_pb[0] - w0), A + 544, j);
+      }
+    }
+    __syncwarp();
+    {  // up1: [34][8] -> [17][16]
+      const int f = lane >> 3, j = lane & 7;
+      if (lane < 8 * DEC2_FW && f < nf) {
+        float* A = base + f * DEC2_FR;
+        dec2_layer<2 * H, H, HP, 8, true>(A + 544, wts + (L.dec_w[1] - w0), wts + (L.dec_pb[1] - w0), A, j);
+      }
+    }
+    __syncwarp();
+    {  // up2: [34][16] -> [17][32]
+      const int f = lane >> 4, j = lane & 15;
+      if (f < nf) {
+        float* A = base + f * DEC2_FR;
+        dec2_layer<2 * H, H, HP, 16, true>(A, wts + (L.dec_w[2] - w0), wts + (L.dec_pb[2] - w0), A + 544, j);
+      }
+    }
+    __syncwarp();
+    for (int f = 0; f < nf; ++f) {  // up3: [34][32] -> [1][64]
+      float* A = base + f * DEC2_FR;
+      dec2_layer<2 * H, 1, 4, 32, false>(A + 544, wts + (L.dec_w[3] - w0), wts + (L.dec_pb[3] - w0), A, lane);
+    }
+    __syncwarp();
+    for (int f = 0; f < nf; ++f) {
+      const float* A = base + f * DEC2_FR;
+      const size_t fr = f0 + f;
+      for (int i = lane; i < NMEL; i += 32) {
+        const float p = A[i];
+        pred[fr * NMEL + i] = p;
+        if (fused_mode) {
+          const float xv = x[fr * NMEL + i];
+          float v;
+          if (fused_mode == 1) {
+            float r = xv - p;
+            r = r > 0.f ? r : 0.2f * r;
+            v = fmaxf(expm1f(r), 0.f);
+          } else {
+            v = expf(xv - fmaxf(p, 0.f) * out_scale) - 1.0f;
+          }
+          mel[fr * NMEL + i] = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void scale_kernel(float* p, size_t n, float s) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] *= s;
@@ -488,12 +640,21 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   B2D_LAUNCH_CHECK("recurrence_kernel");
   if (conv_mode == 0) {
     const int nw = L.total - L.dec_w[0];
-    const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC_WARPS * DEC_ACT);
-    B2D_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t want = (nf + DEC_WARPS - 1) / DEC_WARPS;
-    const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
-    decoder_kernel<<<grid, DEC_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
-    B2D_LAUNCH_CHECK("decoder_kernel");
+    if (getenv("B2D_DECODER_V1")) {
+      const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC_WARPS * DEC_ACT);
+      B2D_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t want = (nf + DEC_WARPS - 1) / DEC_WARPS;
+      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
+      decoder_kernel<<<grid, DEC_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
+      B2D_LAUNCH_CHECK("decoder_kernel");
+    } else {
+      const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC2_WARPS * DEC2_FW * DEC2_FR);
+      B2D_CUDA(cudaFuncSetAttribute(decoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t want = (nf + DEC2_WARPS * DEC2_FW - 1) / (DEC2_WARPS * DEC2_FW);
+      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
+      decoder2_kernel<<<grid, DEC2_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
+      B2D_LAUNCH_CHECK("decoder2_kernel");
+    }
   } else {
     int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, dec_scratch, st);
     if (rc != B2D_OK) return rc;
