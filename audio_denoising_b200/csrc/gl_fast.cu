@@ -54,6 +54,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // per-warp shared-memory staging: exchange buffer | tprev row | mag row | mbarrier
 constexpr int MAG_ROW_BYTES = (M + 4) * 4;                      // Fp floats = 2064 B
 constexpr int WARP_SMEM = XCH * 8 + M * 8 + 2080 + 16;          // 10800 B, 16-byte multiple
+constexpr int WARP_SMEM_X = WARP_SMEM + 2 * HOP * 4 + 16;       // + two hop-block buffers and their mbarriers (XTMA variant)
 
 // same partial-format helpers as the generic kernel (griffinlim.cu); only used for the two reflect-padded
 // edge blocks of a clip (j == 0 and j == T), through a compact non-unrolled loop
@@ -71,7 +72,7 @@ __device__ __noinline__ void stage_reflect_block(const float* __restrict__ part,
   }
 }
 
-template <int WARPS, int MINB, bool USE_PREV>
+template <int WARPS, int MINB, bool USE_PREV, bool XTMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFastArgs a) {
   // tables (float2 views): WA[256] = inv_env*win (first half), WB[256] = inv_env*win (second half),
   // WN[512] = win/N, RT[512] = W1024^k ; per-warp exchange buffers behind them
@@ -98,13 +99,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   const int b = gw / a.R, r = gw - b * a.R;
   const int n = a.n, R = a.R, T = a.T;
   const int tb = r * n, te = min(T, tb + n);
-  unsigned char* wsm = warp_base + (size_t)warp * WARP_SMEM;
+  unsigned char* wsm = warp_base + (size_t)warp * (XTMA ? WARP_SMEM_X : WARP_SMEM);
   float2* S = reinterpret_cast<float2*>(wsm);                       // exchange buffer
   float2* tp_s = reinterpret_cast<float2*>(wsm + XCH * 8);          // staged tprev row of the current frame
   float* mg_s = reinterpret_cast<float*>(wsm + XCH * 8 + M * 8);    // staged mag row
   uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + XCH * 8 + M * 8 + 2080);
+  float* xs = reinterpret_cast<float*>(wsm + WARP_SMEM);            // XTMA: ring of two hop-blocks of the iterate
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(wsm + WARP_SMEM + 2 * HOP * 4);
   if (lane == 0) {
     mbar_init(bar, 1);
+    if (XTMA) { mbar_init(xbar, 1); mbar_init(xbar + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -126,11 +130,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
     bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, MAG_ROW_BYTES, bar);
     if (USE_PREV) bulk_g2s(tp_s, a.tprev + ((size_t)b * T + tb) * M, M * 8, bar);
   }
+  const int nrun = te - tb;
+  if (XTMA && lane == 0 && nrun > 1) {  // own-slot hop-blocks 1 .. nrun-1 travel by TMA, one frame ahead
+    mbar_expect_tx(xbar + 1, HOP * 4);
+    bulk_g2s(xs + HOP, xrun + HOP, HOP * 4, xbar + 1);
+  }
 #pragma unroll 1
   for (int t = tb; t < te; ++t) {
     const int c = t - tb;
     float2 v[16];
-    if (t + 2 < te && lane < 16) prefetch_l2(xrun + (size_t)(c + 2) * HOP + lane * 32);  // next frame's new hop-block
+    if (!XTMA && t + 2 < te && lane < 16) prefetch_l2(xrun + (size_t)(c + 2) * HOP + lane * 32);  // next frame's new hop-block
     // ---- stage the frame: hop-blocks t (first half) and t+1 (second half), envelope + window applied ---
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -143,6 +152,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[8 * h + q] = S[lane + 32 * q];
+      } else if (XTMA && cs >= 1 && cs <= nrun - 1) {  // interior block of this run: already in the shared-memory ring
+        if (h == 1) mbar_wait(xbar + (cs & 1), ((cs - 1) >> 1) & 1);  // k-th use of this barrier; (h == 0: awaited one frame ago)
+        const float2* src = reinterpret_cast<const float2*>(xs + (cs & 1) * HOP);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 xv = src[lane + 32 * q];
+          const float2 wv = wtab[lane + 32 * q];
+          v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
       } else {
         const float2* p1 = reinterpret_cast<const float2*>(xrun + (size_t)cs * HOP);
         const float2* p2 = nullptr;   // second partial when the block sits on a run boundary
@@ -155,6 +173,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
           const float2 wv = wtab[lane + 32 * q];
           v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
         }
+      }
+    }
+    if (XTMA) {  // block c is consumed: its buffer takes block c+2 while this frame computes
+      __syncwarp();
+      if (lane == 0 && c + 2 <= nrun - 1) {
+        mbar_expect_tx(xbar + (c & 1), HOP * 4);
+        bulk_g2s(xs + (c & 1) * HOP, xrun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
       }
     }
     // ---- forward FFT ------------------------------------------------------------------------------------
@@ -464,17 +489,17 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   return B2D_OK;
 }
 
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool XTMA>
 static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
   const int runs = a.B * a.R;
-  const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)WARPS * WARP_SMEM;
+  const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)WARPS * (XTMA ? WARP_SMEM_X : WARP_SMEM);
   const dim3 grid((runs + WARPS - 1) / WARPS), block(WARPS * 32);
   if (a.use_prev) {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, true><<<grid, block, smem, st>>>(a);
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true, XTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, true, XTMA><<<grid, block, smem, st>>>(a);
   } else {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, false><<<grid, block, smem, st>>>(a);
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false, XTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, false, XTMA><<<grid, block, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("gl_fast512_kernel");
   return B2D_OK;
@@ -482,8 +507,8 @@ static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
 
 int gl_fast_warps_per_sm() {
   const char* e = getenv("B2D_GL_VARIANT");
-  const int v = e ? atoi(e) : 0;
-  return v == 1 ? 12 : 16;
+  const int v = e ? atoi(e) : 3;
+  return (v == 1 || v == 3) ? 12 : 16;
 }
 
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
@@ -494,10 +519,11 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
   a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev;
   const char* e = getenv("B2D_GL_VARIANT");
-  const int variant = e ? atoi(e) : 0;
-  if (variant == 1) return launch_variant<4, 3>(a, st);   // 12 warps/SM, up to 168 registers
-  if (variant == 2) return launch_variant<4, 4>(a, st);   // 16 warps/SM in 4-warp CTAs
-  return launch_variant<8, 2>(a, st);                     // 16 warps/SM in 8-warp CTAs
+  const int variant = e ? atoi(e) : 3;  // default: 12 warps/SM, tprev / mag / iterate all staged by TMA
+  if (variant == 1) return launch_variant<4, 3, false>(a, st);   // 12 warps/SM, up to 168 registers
+  if (variant == 2) return launch_variant<4, 4, false>(a, st);   // 16 warps/SM in 4-warp CTAs
+  if (variant == 0) return launch_variant<8, 2, false>(a, st);   // 16 warps/SM in 8-warp CTAs
+  return launch_variant<6, 2, true>(a, st);                      // 12 warps/SM, iterate hop-blocks by TMA as well
 }
 
 }  // namespace b2d

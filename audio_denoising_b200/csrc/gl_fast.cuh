@@ -167,7 +167,9 @@ B2D_HD int slot_k(int lane, int r) { return (lane == 0 && r >= 4) ? 32 + 64 * (r
 // |a| -> 0 both forms tend to a * 1e16 (and give exactly 0 for a == 0, e.g. digital silence).
 B2D_HD float inv_norm(float s) {
 #ifdef __CUDA_ARCH__
-  return rsqrtf(fmaxf(s, 1e-32f));
+  float r;  // the clamp keeps the argument a normal number: the flush-to-zero approximate unit (one MUFU) is exact enough
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 1e-32f)));
+  return r;
 #else
   return 1.0f / sqrtf(fmaxf(s, 1e-32f));
 #endif
@@ -177,11 +179,21 @@ B2D_HD float2 unit_dir_fast(float2 a) {
   return make_float2(a.x * inv, a.y * inv);
 }
 
+// rfft_split without the factor 1/2: returns 2 X[k], 2 X[M-k].  The fast path keeps 2 * rebuilt in tprev: the phase
+// update only uses the direction of (rebuilt - m * tprev), which is invariant to the common factor.
+B2D_HD void rfft_split2(float2 zk, float2 zmk, float2 rt, float2& xk, float2& xmk) {
+  const float ex = zk.x + zmk.x, ey = zk.y - zmk.y;
+  const float dx = zk.x - zmk.x, dy = zk.y + zmk.y;
+  const float tx = fmaf(rt.x, dx, -rt.y * dy), ty = fmaf(rt.x, dy, rt.y * dx);
+  xk = make_float2(ex + ty, ey - tx);
+  xmk = make_float2(ex - ty, -ey - tx);
+}
+
 // One pair slot: split -> momentum/projection -> (store rebuilt) -> magnitude -> merge, in place.
 // pk/pmk: previous rebuilt values at k and M-k (ignored unless use_prev); returns rebuilt values in xk/xmk.
 B2D_HD void pair_update(float2& U, float2& V, float2 rt, float2 pk, float2 pmk, float mk, float mmk, float mom,
                         bool use_prev, float2& xk, float2& xmk) {
-  rfft_split(U, V, rt, xk, xmk);
+  rfft_split2(U, V, rt, xk, xmk);
   float2 ak = xk, amk = xmk;
   if (use_prev) {
     ak = make_float2(fmaf(-mom, pk.x, xk.x), fmaf(-mom, pk.y, xk.y));
@@ -195,9 +207,9 @@ B2D_HD void pair_update(float2& U, float2& V, float2 rt, float2 pk, float2 pmk, 
 // p0 = (Re P[0], Re P[M]) packed, p256 = P[256]; m0, mM, m256 magnitudes.  Returns packed rebuilt values.
 B2D_HD void special_update(float2& U, float2& V, float2 p0, float2 p256, float m0, float mM, float m256, float mom,
                            bool use_prev, float2& x0M, float2& x256) {
-  const float X0 = U.x + U.y, XM = U.x - U.y;
+  const float X0 = 2.0f * (U.x + U.y), XM = 2.0f * (U.x - U.y);  // 2 * rebuilt, like rfft_split2
   x0M = make_float2(X0, XM);
-  x256 = make_float2(V.x, -V.y);
+  x256 = make_float2(2.0f * V.x, -2.0f * V.y);
   float a0 = X0, aM = XM;
   float2 a256 = x256;
   if (use_prev) {

@@ -71,8 +71,8 @@ int main() {
   std::vector<cd> X(M + 1), Y(M + 1);
   for (int k = 0; k <= M; ++k) { cd a = 0; for (int n = 0; n < N; ++n) a += (double)x[n] * std::polar(1.0, -2 * M_PI * (double)((long)n * k % N) / N); X[k] = a; }
   for (int k = 0; k <= M; ++k) {
-    cd p = (k == 0) ? cd(P[0].x, 0) : (k == M) ? cd(P[0].y, 0) : cd(P[k].x, P[k].y);
-    cd a = X[k] - (double)mom * p;
+    cd p = (k == 0) ? cd(P[0].x, 0) : (k == M) ? cd(P[0].y, 0) : cd(P[k].x, P[k].y);  // P = 2 * previous rebuilt
+    cd a = 2.0 * X[k] - (double)mom * p;
     if (k == 0 || k == M) a = cd(a.real(), 0);
     Y[k] = (double)mag[k] * a / (std::abs(a) + 1e-16);
   }
@@ -106,8 +106,8 @@ int main() {
   }
   for (int k = 0; k < M; ++k) if (stored[k] != 1) { printf("tprev bin %d stored %d times\n", k, stored[k]); bad++; }
   e = 0; nrm = 0;
-  for (int k = 1; k < M; ++k) { e += std::norm(cd(newP[k].x, newP[k].y) - X[k]); nrm += std::norm(X[k]); }
-  e += std::norm(cd(newP[0].x, 0) - X[0]) + std::norm(cd(newP[0].y, 0) - X[M]);
+  for (int k = 1; k < M; ++k) { e += std::norm(cd(newP[k].x, newP[k].y) - 2.0 * X[k]); nrm += std::norm(2.0 * X[k]); }  // tprev holds 2 * rebuilt
+  e += std::norm(cd(newP[0].x, 0) - 2.0 * X[0]) + std::norm(cd(newP[0].y, 0) - 2.0 * X[M]);
   printf("rebuilt (tprev) rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 2e-6) bad++;
   inverse();
   e = 0; nrm = 0;
