@@ -72,7 +72,7 @@ __device__ __noinline__ void stage_reflect_block(const float* __restrict__ part,
   }
 }
 
-template <int WARPS, int MINB, bool USE_PREV, bool XTMA>
+template <int WARPS, int MINB, bool USE_PREV, bool XTMA, bool PERSIST>
 __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFastArgs a) {
   // tables (float2 views): WA[256] = inv_env*win (first half), WB[256] = inv_env*win (second half),
   // WN[512] = win/N, RT[512] = W1024^k ; per-warp exchange buffers behind them
@@ -94,11 +94,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * WARPS + warp;
-  if (gw >= a.B * a.R) return;
-  const int b = gw / a.R, r = gw - b * a.R;
   const int n = a.n, R = a.R, T = a.T;
-  const int tb = r * n, te = min(T, tb + n);
+  const int nruns = a.B * a.R;
+  // PERSIST: one CTA per SM; run ids are dealt round-robin over the CTAs first, so every SM carries the same number
+  // of busy warps (+-1).  Otherwise: consecutive warps of consecutive CTAs.
+  const int gw0 = PERSIST ? warp * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x * WARPS + warp;
+  const int gstep = PERSIST ? WARPS * (int)gridDim.x : nruns;
+  if (gw0 >= nruns) return;
   unsigned char* wsm = warp_base + (size_t)warp * (XTMA ? WARP_SMEM_X : WARP_SMEM);
   float2* S = reinterpret_cast<float2*>(wsm);                       // exchange buffer
   float2* tp_s = reinterpret_cast<float2*>(wsm + XCH * 8);          // staged tprev row of the current frame
@@ -116,8 +118,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   lane_twiddles(lane, a.tw512, tw);
   // lane 0 owns families 0 and 32: its slots r >= 4 sit 224 bins below the regular lane + 64 r pattern
   const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
-
   const size_t run_stride = (size_t)(n + 1) * HOP;
+  uint32_t tma_uses = 0, xuse0 = 0, xuse1 = 0;  // completed phases of the three mbarriers (parity tracking across runs)
+
+#pragma unroll 1
+  for (int gw = gw0; gw < nruns; gw += gstep) {
+  const int b = gw / R, r = gw - b * R;
+  const int tb = r * n, te = min(T, tb + n);
   const float* xrun = a.xin + (size_t)(b * R + r) * run_stride;
   float* xo = a.xout + (size_t)(b * R + r) * run_stride;
   float2 carry[8];
@@ -153,7 +160,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[8 * h + q] = S[lane + 32 * q];
       } else if (XTMA && cs >= 1 && cs <= nrun - 1) {  // interior block of this run: already in the shared-memory ring
-        if (h == 1) mbar_wait(xbar + (cs & 1), ((cs - 1) >> 1) & 1);  // k-th use of this barrier; (h == 0: awaited one frame ago)
+        if (h == 1) {  // (h == 0: the same block was awaited one frame ago)
+          if (cs & 1) { mbar_wait(xbar + 1, xuse1 & 1); ++xuse1; } else { mbar_wait(xbar, xuse0 & 1); ++xuse0; }
+        }
         const float2* src = reinterpret_cast<const float2*>(xs + (cs & 1) * HOP);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -193,7 +202,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
     fwd3_load(lane, v, S);
     // ---- spectral update (tprev / mag rows were bulk-copied into smem one frame ahead) -----------------------
     float2* tp = a.tprev + ((size_t)b * T + t) * M;
-    mbar_wait(bar, c & 1);
+    mbar_wait(bar, tma_uses & 1);
+    ++tma_uses;
     if (lane == 0) lane0_permute(v);
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
@@ -240,6 +250,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   float2* dst = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
 #pragma unroll
   for (int q = 0; q < 8; ++q) dst[lane + 32 * q] = carry[q];
+  __syncwarp();
+  }  // next run of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -489,17 +501,18 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   return B2D_OK;
 }
 
-template <int WARPS, int MINB, bool XTMA>
-static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
+template <int WARPS, int MINB, bool XTMA, bool PERSIST>
+static int launch_variant(const GlFastArgs& a, int num_sms, cudaStream_t st) {
   const int runs = a.B * a.R;
   const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)WARPS * (XTMA ? WARP_SMEM_X : WARP_SMEM);
-  const dim3 grid((runs + WARPS - 1) / WARPS), block(WARPS * 32);
+  const int ctas = (runs + WARPS - 1) / WARPS;
+  const dim3 grid(PERSIST ? (runs < num_sms ? runs : num_sms) : ctas), block(WARPS * 32);
   if (a.use_prev) {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true, XTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, true, XTMA><<<grid, block, smem, st>>>(a);
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true, XTMA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, true, XTMA, PERSIST><<<grid, block, smem, st>>>(a);
   } else {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false, XTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, false, XTMA><<<grid, block, smem, st>>>(a);
+    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false, XTMA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gl_fast512_kernel<WARPS, MINB, false, XTMA, PERSIST><<<grid, block, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("gl_fast512_kernel");
   return B2D_OK;
@@ -507,8 +520,12 @@ static int launch_variant(const GlFastArgs& a, cudaStream_t st) {
 
 int gl_fast_warps_per_sm() {
   const char* e = getenv("B2D_GL_VARIANT");
-  const int v = e ? atoi(e) : 3;
-  return (v == 1 || v == 3) ? 12 : 16;
+  const int v = e ? atoi(e) : 4;
+  return (v == 0 || v == 2) ? 16 : 12;
+}
+bool gl_fast_persistent() {
+  const char* e = getenv("B2D_GL_VARIANT");
+  return (e ? atoi(e) : 4) == 4;
 }
 
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
@@ -519,11 +536,12 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
   a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev;
   const char* e = getenv("B2D_GL_VARIANT");
-  const int variant = e ? atoi(e) : 3;  // default: 12 warps/SM, tprev / mag / iterate all staged by TMA
-  if (variant == 1) return launch_variant<4, 3, false>(a, st);   // 12 warps/SM, up to 168 registers
-  if (variant == 2) return launch_variant<4, 4, false>(a, st);   // 16 warps/SM in 4-warp CTAs
-  if (variant == 0) return launch_variant<8, 2, false>(a, st);   // 16 warps/SM in 8-warp CTAs
-  return launch_variant<6, 2, true>(a, st);                      // 12 warps/SM, iterate hop-blocks by TMA as well
+  const int variant = e ? atoi(e) : 4;  // default: persistent, 12 warps/SM, tprev / mag / iterate all staged by TMA
+  if (variant == 1) return launch_variant<4, 3, false, false>(a, p->num_sms, st);   // 12 warps/SM, up to 168 registers
+  if (variant == 2) return launch_variant<4, 4, false, false>(a, p->num_sms, st);   // 16 warps/SM in 4-warp CTAs
+  if (variant == 0) return launch_variant<8, 2, false, false>(a, p->num_sms, st);   // 16 warps/SM in 8-warp CTAs
+  if (variant == 3) return launch_variant<6, 2, true, false>(a, p->num_sms, st);    // 12 warps/SM, iterate hop-blocks by TMA too
+  return launch_variant<12, 1, true, true>(a, p->num_sms, st);                      // one 12-warp CTA per SM, runs dealt evenly
 }
 
 }  // namespace b2d

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict_
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
                       int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast.cu
 int gl_fast_warps_per_sm();
+bool gl_fast_persistent();
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            cudaStream_t st);
 
@@ -219,11 +220,30 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   q.G = (p->M <= 1024) ? 4 : 2;
   q.fast = (p->n_fft == 1024 && p->hop == 512 && getenv("B2D_GL_GENERIC") == nullptr);
   if (q.fast) {
-    // one warp per run; 16 warps resident per SM (2 CTAs x 8 warps): aim for a single, nearly full wave
-    const long slots = (long)gl_fast_warps_per_sm() * p->num_sms;
+    // one warp per run.  Pick the number of runs per clip R that minimises the busiest SM's load
+    // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
+    const int wps = gl_fast_warps_per_sm();
+    const long slots = (long)wps * p->num_sms;
+    const int maxR = (T + 3) / 4;  // at least 4 frames per run
+    if (gl_fast_persistent()) {
+      // Measured: a warp needs ~4.5 us per frame whether 1 or 12 warps share the SM (the kernel is latency-bound per
+      // warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).  Minimise that; ties -> longer runs
+      // (less boundary traffic).
+      long best = -1; int bestR = 1;
+      for (int R = 1; R <= maxR; ++R) {
+        const int n = (T + R - 1) / R;
+        const int Reff = (T + n - 1) / n;
+        const long runs = (long)B * Reff;
+        const long rounds = (runs + slots - 1) / slots;
+        const long cost = rounds * n;
+        if (best < 0 || cost < best) { best = cost; bestR = Reff; }
+      }
+      q.n = (T + bestR - 1) / bestR;
+      q.R = (T + q.n - 1) / q.n;
+      return q;
+    }
     int R = (int)(slots / B);
     if (R < 1) R = 1;
-    const int maxR = (T + 3) / 4;  // at least 4 frames per run
     if (R > maxR) R = maxR;
     q.n = (T + R - 1) / R;
     q.R = (T + q.n - 1) / q.n;
