@@ -6,13 +6,16 @@ interfaces: ``GRUUNet2`` (gruunet2.py), the five torchaudio-style transforms the
 (app3.py:135-153), and the ``utils`` names.  CUDA only; the package raises if the library is missing.
 """
 from . import _cabi
-from .gruunet2 import GRUUNet2
+from .checkpoint import TrainingContext, load_denoising_model, save_checkpoint
+from .gruunet2 import GRUUNet, GRUUNet2
 from .pipeline import DenoisePipeline, StreamingDenoiser
+from .serving import DenoiseServer
 from .transforms import GriffinLim, InverseMelScale, InverseSpectrogram, MelScale, Spectrogram
 
 __all__ = [
-    "GRUUNet2", "Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram",
-    "DenoisePipeline", "StreamingDenoiser", "native_library",
+    "GRUUNet2", "GRUUNet", "Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram",
+    "DenoisePipeline", "StreamingDenoiser", "DenoiseServer", "TrainingContext", "load_denoising_model", "save_checkpoint",
+    "native_library",
 ]
 __version__ = "0.1.0"
 

@@ -525,7 +525,7 @@ int gl_fast_warps_per_sm() {
 }
 bool gl_fast_persistent() {
   const char* e = getenv("B2D_GL_VARIANT");
-  return (e ? atoi(e) : 4) == 4;
+  return (e ? atoi(e) : 4) >= 4;
 }
 
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
@@ -541,6 +541,7 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
   if (variant == 2) return launch_variant<4, 4, false, false>(a, p->num_sms, st);   // 16 warps/SM in 4-warp CTAs
   if (variant == 0) return launch_variant<8, 2, false, false>(a, p->num_sms, st);   // 16 warps/SM in 8-warp CTAs
   if (variant == 3) return launch_variant<6, 2, true, false>(a, p->num_sms, st);    // 12 warps/SM, iterate hop-blocks by TMA too
+  // (13+ warps per SM put 4 warps on one scheduler partition: 128-register cap -> spills, measured 107-120 us)
   return launch_variant<12, 1, true, true>(a, p->num_sms, st);                      // one 12-warp CTA per SM, runs dealt evenly
 }
 

@@ -144,6 +144,121 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encoder_kernel(const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// encoder, register-tiled (same scheme as decoder2): a warp works on 2 frames; a lane owns one OUTPUT position of
+// one frame (and, in the small layers, a slice of the output channels) and keeps its accumulators in registers.
+// Per input channel: 3 activation loads, 3 broadcast float4 weight loads per channel group, 12 FMAs per group.
+// ------------------------------------------------------------------------------------------------
+constexpr int ENC2_WARPS = 8;
+constexpr int ENC2_FW = 2;
+constexpr int ENC2_FR = ENC_ACT + 12;  // 1232: the two frames of a warp land on different banks
+
+template <int CIN, int COUT, int COP, int LIN, int CSPLIT>
+__device__ __forceinline__ void enc2_layer(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ PB,
+                                           float* __restrict__ out, int j, int cs) {
+  constexpr int LOUT = LIN / 2;
+  constexpr int NG = COP / 4;
+  constexpr int NGL = (NG + CSPLIT - 1) / CSPLIT;
+  const int g0 = cs * NGL;
+  float4 acc[NGL];
+#pragma unroll
+  for (int gl = 0; gl < NGL; ++gl)
+    acc[gl] = ((CSPLIT == 1) || (g0 + gl < NG)) ? *reinterpret_cast<const float4*>(PB + j * COP + 4 * (g0 + gl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool has_l = (j > 0), has_r = (2 * j + 1 < LIN);
+#pragma unroll 2
+  for (int ci = 0; ci < CIN; ++ci) {
+    const float* row = in + ci * LIN + 2 * j;
+    const float a0 = has_l ? row[-1] : 0.f;
+    const float a1 = row[0];
+    const float a2 = has_r ? row[1] : 0.f;
+    const float* w = W + ci * 3 * COP + 4 * g0;
+#pragma unroll
+    for (int gl = 0; gl < NGL; ++gl) {
+      if ((CSPLIT == 1) || (g0 + gl < NG)) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * gl);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + COP + 4 * gl);
+        const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * COP + 4 * gl);
+        acc[gl].x = fmaf(a0, w0.x, fmaf(a1, w1.x, fmaf(a2, w2.x, acc[gl].x)));
+        acc[gl].y = fmaf(a0, w0.y, fmaf(a1, w1.y, fmaf(a2, w2.y, acc[gl].y)));
+        acc[gl].z = fmaf(a0, w0.z, fmaf(a1, w1.z, fmaf(a2, w2.z, acc[gl].z)));
+        acc[gl].w = fmaf(a0, w0.w, fmaf(a1, w1.w, fmaf(a2, w2.w, acc[gl].w)));
+      }
+    }
+  }
+#pragma unroll
+  for (int gl = 0; gl < NGL; ++gl) {
+    const float r[4] = {acc[gl].x, acc[gl].y, acc[gl].z, acc[gl].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = 4 * (g0 + gl) + q;
+      if (co < COUT) out[co * LOUT + j] = fmaxf(r[q], 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ENC2_WARPS * 32, 2) encoder2_kernel(const float* __restrict__ blob, const float* __restrict__ x,
+                                                                      size_t nframes, float* __restrict__ d0, float* __restrict__ d1,
+                                                                      float* __restrict__ d2, float* __restrict__ gx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Packed L = packed_layout();
+  float* wts = reinterpret_cast<float*>(smem_raw);
+  const int nw = L.rec_w;
+  float* act = wts + ((nw + 3) & ~3);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = act + warp * (ENC2_FW * ENC2_FR);
+  const size_t stride = (size_t)gridDim.x * ENC2_WARPS * ENC2_FW;
+  for (size_t f0 = ((size_t)blockIdx.x * ENC2_WARPS + warp) * ENC2_FW; f0 < nframes; f0 += stride) {
+    const int nf = (int)min((size_t)ENC2_FW, nframes - f0);
+    if (f0 + stride + ENC2_FW <= nframes) prefetch_l2_range(x + (f0 + stride) * NMEL, ENC2_FW * NMEL * 4, lane);
+    for (int f = 0; f < nf; ++f) {
+      float* a_in = base + f * ENC2_FR;
+      a_in[lane] = x[(f0 + f) * NMEL + lane];
+      a_in[lane + 32] = x[(f0 + f) * NMEL + lane + 32];
+    }
+    __syncwarp();
+    for (int f = 0; f < nf; ++f) {  // L0: [1][64] -> [17][32]   one frame per pass
+      float* a_in = base + f * ENC2_FR;
+      enc2_layer<1, H, HP, 64, 1>(a_in, wts + L.enc_w[0], wts + L.enc_pb[0], a_in + NMEL, lane, 0);
+    }
+    __syncwarp();
+    {  // L1: [17][32] -> [17][16]   lane = f*16 + j
+      const int f = lane >> 4, j = lane & 15;
+      if (f < nf) {
+        float* a0 = base + f * ENC2_FR + NMEL;
+        enc2_layer<H, H, HP, 32, 1>(a0, wts + L.enc_w[1], wts + L.enc_pb[1], a0 + D0, j, 0);
+      }
+    }
+    __syncwarp();
+    {  // L2: [17][16] -> [17][8]    lane = f*16 + j*2 + channel split
+      const int f = lane >> 4, j = (lane >> 1) & 7, cs = lane & 1;
+      if (f < nf) {
+        float* a1 = base + f * ENC2_FR + NMEL + D0;
+        enc2_layer<H, H, HP, 16, 2>(a1, wts + L.enc_w[2], wts + L.enc_pb[2], a1 + D1, j, cs);
+      }
+    }
+    __syncwarp();
+    {  // L3: [17][8] -> [51][4]     lane = f*16 + j*4 + channel split (13 groups over 4 lanes)
+      const int f = lane >> 4, j = (lane >> 2) & 3, cs = lane & 3;
+      if (f < nf) {
+        float* a2 = base + f * ENC2_FR + NMEL + D0 + D1;
+        enc2_layer<H, H3, H3P, 8, 4>(a2, wts + L.enc_w[3], wts + L.enc_pb[3], a2 + D2, j, cs);
+      }
+    }
+    __syncwarp();
+    for (int f = 0; f < nf; ++f) {
+      const float* a0 = base + f * ENC2_FR + NMEL;
+      const size_t fr = f0 + f;
+      for (int i = lane; i < D0; i += 32) d0[fr * D0 + i] = a0[i];
+      for (int i = lane; i < D1; i += 32) d1[fr * D1 + i] = a0[D0 + i];
+      for (int i = lane; i < D2; i += 32) d2[fr * D2 + i] = a0[D0 + D1 + i];
+      for (int i = lane; i < GX; i += 32) gx[fr * GX + i] = a0[D0 + D1 + D2 + i];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // recurrence: one CTA (96 threads, 68 active) per clip; thread (c, j) owns hidden channel c at
 // compressed bin j and keeps its 3 x 17 x 3 recurrent weights in registers for all T steps.
 // ------------------------------------------------------------------------------------------------
@@ -334,40 +449,47 @@ constexpr int DEC2_WARPS = 6;
 constexpr int DEC2_FW = 2;
 constexpr int DEC2_FR = 544 + 1088 + 16;  // +16: the two frames of a warp land on different banks
 
-template <int CIN, int COUT, int COP, int LIN, bool RELU>
+// CSPLIT lanes share one (frame, j): lane `cs` computes the output-channel groups [cs*NGL, (cs+1)*NGL) -- keeps all 32
+// lanes busy in the small layers (up0: 2 frames x 4 positions x 4 splits, up1: 2 x 8 x 2).
+template <int CIN, int COUT, int COP, int LIN, int CSPLIT, bool RELU>
 __device__ __forceinline__ void dec2_layer(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ PB,
-                                           float* __restrict__ out, int j) {
+                                           float* __restrict__ out, int j, int cs) {
   constexpr int NG = COP / 4;
-  float4 ae[NG], ao[NG];
+  constexpr int NGL = (NG + CSPLIT - 1) / CSPLIT;
+  const int g0 = cs * NGL;
+  float4 ae[NGL], ao[NGL];
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    ae[g] = *reinterpret_cast<const float4*>(PB + (2 * j) * COP + 4 * g);
-    ao[g] = *reinterpret_cast<const float4*>(PB + (2 * j + 1) * COP + 4 * g);
+  for (int gl = 0; gl < NGL; ++gl) {
+    const bool on = (CSPLIT == 1) || (g0 + gl < NG);
+    ae[gl] = on ? *reinterpret_cast<const float4*>(PB + (2 * j) * COP + 4 * (g0 + gl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ao[gl] = on ? *reinterpret_cast<const float4*>(PB + (2 * j + 1) * COP + 4 * (g0 + gl)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const bool has_next = (j + 1 < LIN);
 #pragma unroll 2
   for (int ci = 0; ci < CIN; ++ci) {
     const float a0 = in[ci * LIN + j];
     const float a1 = has_next ? in[ci * LIN + j + 1] : 0.f;
-    const float* w = W + ci * 3 * COP;
+    const float* w = W + ci * 3 * COP + 4 * g0;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * g);
-      const float4 w1 = *reinterpret_cast<const float4*>(w + COP + 4 * g);
-      const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * COP + 4 * g);
-      ae[g].x = fmaf(a0, w1.x, ae[g].x); ae[g].y = fmaf(a0, w1.y, ae[g].y);
-      ae[g].z = fmaf(a0, w1.z, ae[g].z); ae[g].w = fmaf(a0, w1.w, ae[g].w);
-      ao[g].x = fmaf(a0, w2.x, fmaf(a1, w0.x, ao[g].x)); ao[g].y = fmaf(a0, w2.y, fmaf(a1, w0.y, ao[g].y));
-      ao[g].z = fmaf(a0, w2.z, fmaf(a1, w0.z, ao[g].z)); ao[g].w = fmaf(a0, w2.w, fmaf(a1, w0.w, ao[g].w));
+    for (int gl = 0; gl < NGL; ++gl) {
+      if ((CSPLIT == 1) || (g0 + gl < NG)) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * gl);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + COP + 4 * gl);
+        const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * COP + 4 * gl);
+        ae[gl].x = fmaf(a0, w1.x, ae[gl].x); ae[gl].y = fmaf(a0, w1.y, ae[gl].y);
+        ae[gl].z = fmaf(a0, w1.z, ae[gl].z); ae[gl].w = fmaf(a0, w1.w, ae[gl].w);
+        ao[gl].x = fmaf(a0, w2.x, fmaf(a1, w0.x, ao[gl].x)); ao[gl].y = fmaf(a0, w2.y, fmaf(a1, w0.y, ao[gl].y));
+        ao[gl].z = fmaf(a0, w2.z, fmaf(a1, w0.z, ao[gl].z)); ao[gl].w = fmaf(a0, w2.w, fmaf(a1, w0.w, ao[gl].w));
+      }
     }
   }
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const float e[4] = {ae[g].x, ae[g].y, ae[g].z, ae[g].w};
-    const float o[4] = {ao[g].x, ao[g].y, ao[g].z, ao[g].w};
+  for (int gl = 0; gl < NGL; ++gl) {
+    const float e[4] = {ae[gl].x, ae[gl].y, ae[gl].z, ae[gl].w};
+    const float o[4] = {ao[gl].x, ao[gl].y, ao[gl].z, ao[gl].w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int co = 4 * g + q;
+      const int co = 4 * (g0 + gl) + q;
       if (co < COUT) {
         float2 r = make_float2(e[q], o[q]);
         if (RELU) r = make_float2(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f));
@@ -414,19 +536,19 @@ __global__ void __launch_bounds__(DEC2_WARPS * 32, 2) decoder2_kernel(const floa
       for (int i = lane; i < D0; i += 32) Bq[H * 32 + i] = d0[fr * D0 + i];         // s3 upper half
     }
     __syncwarp();
-    {  // up0: [17][4] -> [17][8]   (lanes f*4 + j)
-      const int f = lane >> 2, j = lane & 3;
-      if (lane < 4 * DEC2_FW && f < nf) {
+    {  // up0: [17][4] -> [17][8]   lane = f*16 + j*4 + channel split (4 ways)
+      const int f = lane >> 4, j = (lane >> 2) & 3, cs = lane & 3;
+      if (f < nf) {
         float* A = base + f * DEC2_FR;
-        dec2_layer<H, H, HP, 4, true>(A, wts + (L.dec_w[0] - w0), wts + (L.dec_pb[0] - w0), A + 544, j);
+        dec2_layer<H, H, HP, 4, 4, true>(A, wts + (L.dec_w[0] - w0), wts + (L.dec_pb[0] - w0), A + 544, j, cs);
       }
     }
     __syncwarp();
-    {  // up1: [34][8] -> [17][16]
-      const int f = lane >> 3, j = lane & 7;
-      if (lane < 8 * DEC2_FW && f < nf) {
+    {  // up1: [34][8] -> [17][16]  lane = f*16 + j*2 + channel split (2 ways)
+      const int f = lane >> 4, j = (lane >> 1) & 7, cs = lane & 1;
+      if (f < nf) {
         float* A = base + f * DEC2_FR;
-        dec2_layer<2 * H, H, HP, 8, true>(A + 544, wts + (L.dec_w[1] - w0), wts + (L.dec_pb[1] - w0), A, j);
+        dec2_layer<2 * H, H, HP, 8, 2, true>(A + 544, wts + (L.dec_w[1] - w0), wts + (L.dec_pb[1] - w0), A, j, cs);
       }
     }
     __syncwarp();
@@ -434,13 +556,13 @@ __global__ void __launch_bounds__(DEC2_WARPS * 32, 2) decoder2_kernel(const floa
       const int f = lane >> 4, j = lane & 15;
       if (f < nf) {
         float* A = base + f * DEC2_FR;
-        dec2_layer<2 * H, H, HP, 16, true>(A, wts + (L.dec_w[2] - w0), wts + (L.dec_pb[2] - w0), A + 544, j);
+        dec2_layer<2 * H, H, HP, 16, 1, true>(A, wts + (L.dec_w[2] - w0), wts + (L.dec_pb[2] - w0), A + 544, j, 0);
       }
     }
     __syncwarp();
     for (int f = 0; f < nf; ++f) {  // up3: [34][32] -> [1][64]
       float* A = base + f * DEC2_FR;
-      dec2_layer<2 * H, 1, 4, 32, false>(A + 544, wts + (L.dec_w[3] - w0), wts + (L.dec_pb[3] - w0), A, lane);
+      dec2_layer<2 * H, 1, 4, 32, 1, false>(A + 544, wts + (L.dec_w[3] - w0), wts + (L.dec_pb[3] - w0), A, lane, 0);
     }
     __syncwarp();
     for (int f = 0; f < nf; ++f) {
@@ -626,12 +748,21 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   const Packed L = packed_layout();
   int dev_sms = 148;
   if (conv_mode == 0) {
-    const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
-    B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
-    const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
-    encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
-    B2D_LAUNCH_CHECK("encoder_kernel");
+    if (getenv("B2D_ENCODER_V2") == nullptr) {  // v1 measures 25 us faster: both are bound by shared-memory weight loads
+      const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
+      B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
+      const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
+      encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
+      B2D_LAUNCH_CHECK("encoder_kernel");
+    } else {
+      const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC2_WARPS * ENC2_FW * ENC2_FR);
+      B2D_CUDA(cudaFuncSetAttribute(encoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t want = (nf + ENC2_WARPS * ENC2_FW - 1) / (ENC2_WARPS * ENC2_FW);
+      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
+      encoder2_kernel<<<grid, ENC2_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
+      B2D_LAUNCH_CHECK("encoder2_kernel");
+    }
   } else {
     int rc = model_forward_tc(m, x, nf, d0, d1, d2, gx, conv_mode, st);
     if (rc != B2D_OK) return rc;

@@ -168,3 +168,8 @@ class GRUUNet2(nn.Module):
         if two_dimmed:
             out = out.squeeze(0)
         return out, h
+
+
+class GRUUNet(GRUUNet2):
+    """``gruunet.GRUUNet`` (gruunet.py): the same network as GRUUNet2 -- the two files differ only in the class name and an
+    unused ``prev`` argument of ``_gruunet`` -- so it shares the kernels."""

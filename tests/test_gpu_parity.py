@@ -471,3 +471,46 @@ def test_pipeline_tensor_core_mode_within_budget(dev):
     a = metrics.si_sdr(r["wave"].cpu(), clean[:, :Lout])
     b = metrics.si_sdr(ref["wave"], clean[:, :Lout])
     assert (a - b).abs().max() <= 0.05
+
+
+# ---------------------------------------------------------------------------------------------- server loop (section 8f rank 1)
+def test_server_request_handler_and_wire_protocol(dev, golden):
+    """DenoiseServer.handle == server.py:199-220 on [n, channels] arrays; then the same through a real Listener/Client pair."""
+    import threading
+    from multiprocessing.connection import Client
+
+    import audio_denoising_b200 as adb
+
+    _, metrics, *_ = _oracle()
+    s = golden("server_chain.npz")
+    m, *_ = _our_model("good", dev)
+    srv = adb.DenoiseServer(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=48000)
+    X = np.stack([s["x"][0], -s["x"][0]], axis=1)  # [n, 2]: only channel 0 is used, answer is repeated over channels
+    for rep in range(2):
+        O = srv.handle(X)
+        assert O.shape == (s[f"wave{rep}"].shape[1], 2) and np.array_equal(O[:, 0], O[:, 1])
+        assert metrics.si_sdr(torch.from_numpy(O[:, 0]), torch.from_numpy(s[f"wave{rep}"][0])) >= 70.0
+    assert metrics.rel_l2(srv.hx.cpu(), torch.from_numpy(s["hx1"])) < 1e-5
+    # wire protocol: pickled ndarray in, ndarray out, hx carried across requests, 'close' ends the connection
+    srv2 = adb.DenoiseServer(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=48000)
+    address = ("localhost", 6117)
+    t = threading.Thread(target=srv2.serve_forever, kwargs=dict(address=address, max_requests=2), daemon=True)
+    t.start()
+    conn = None
+    for _ in range(100):
+        try:
+            conn = Client(address)
+            break
+        except ConnectionRefusedError:
+            import time
+
+            time.sleep(0.05)
+    assert conn is not None
+    outs = []
+    for rep in range(2):
+        conn.send(s["x"][0].reshape(-1, 1))
+        outs.append(conn.recv())
+    conn.close()
+    t.join(timeout=20)
+    for rep in range(2):
+        assert metrics.si_sdr(torch.from_numpy(outs[rep][:, 0]), torch.from_numpy(s[f"wave{rep}"][0])) >= 70.0

@@ -164,3 +164,34 @@ def test_host_fft_and_fast_path_index_math():
         assert r.returncode == 0, r.stderr
         r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+
+
+def test_checkpoint_helpers_round_trip(tmp_path):
+    """save_model / TrainingContext.load / loader heuristics (server.py:36-142, app3.py:46-119) against the B200 module."""
+    import audio_denoising_b200 as adb
+
+    sd, cfg = load_weights("good")
+    ctx = adb.TrainingContext(adb.GRUUNet2, device="cpu", **cfg)
+    ctx.inner.load_state_dict(sd)
+    ctx.total_iters, ctx.batch_size = 123, 32
+    ctx.test_loss_record = {0: 0.5, 1: 0.25}
+    path = ctx.save(prefix=str(tmp_path))
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"last_epoch", "loss_record", "loss_metric", "last_target_name", "total_training_iters", "arch",
+                       "last_batch_size", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "config"}
+    assert ck["arch"] == "GRUUNet2" and ck["total_training_iters"] == 123
+    name = os.path.basename(os.path.dirname(path))
+    back = adb.TrainingContext.load(name, adb.GRUUNet2, prefix=str(tmp_path), device="cpu")
+    assert back.total_iters == 123 and back.batch_size == 32 and back.best_eval_loss == 0.25
+    for k, v in back.inner.state_dict().items():
+        assert torch.equal(v, sd[k])
+    model, dev = adb.load_denoising_model(path, device="cpu")
+    assert isinstance(model, adb.GRUUNet2) and not model.training and dev.type == "cpu"
+    assert adb.load_denoising_model(os.path.join(str(tmp_path), "missing.pth")) == (None, None)  # swallowed like app3.py:118-119
+    with pytest.raises(FileNotFoundError):
+        adb.load_denoising_model(os.path.join(str(tmp_path), "missing.pth"), strict_errors=True)
+    bare = os.path.join(str(tmp_path), "bare.pth")
+    torch.save(dict(sd), bare)  # bare state dict + fallback config (app3.py:71-88)
+    model2, _ = adb.load_denoising_model(bare, fallback_config=cfg, device="cpu")
+    assert model2 is not None
+    assert issubclass(adb.GRUUNet, adb.GRUUNet2)
