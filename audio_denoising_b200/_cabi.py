@@ -67,7 +67,7 @@ SIGNATURES = {
     "b2d_denoise_noisy_phase_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
     "b2d_denoise_noisy_phase": (_i, [_vp, _vp, _vp, _i, _i, _vp, _f, _f, _i, _vp, _vp, _sz, _vp]),
     "b2d_stream_step_workspace_bytes": (_sz, [_vp, _vp, _i]),
-    "b2d_stream_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _u64, _i, _f, _i, _vp, _vp, _sz, _vp]),
+    "b2d_stream_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _u64, _vp, _i, _f, _i, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -30,8 +30,8 @@ bool model_config_supported(const b2d_model_config* c);
 int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv);  // conv_tc.cu
 int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);
 int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
-                     const float2* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
-                     void* ws, size_t ws_bytes, cudaStream_t st);  // stream.cu
+                     const float2* init_angles, unsigned long long seed, const unsigned long long* d_seed, int n_iter, float momentum,
+                     int conv_mode, float* out, void* ws, size_t ws_bytes, cudaStream_t st);  // stream.cu
 size_t stream_step_ws(const b2d_plan* p, const b2d_model* m, int S);
 
 static bool factor(int M, FftDesc& fd) {
@@ -403,10 +403,10 @@ size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* mo
   return stream_step_ws(plan, model, S);
 }
 int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx, float* ola,
-                    const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+                    const b2d_c64* init_angles, unsigned long long seed, const unsigned long long* d_seed, int n_iter,
+                    float momentum, int conv_mode, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   B2D_REQUIRE(plan && model && chunk && hx && ola && out && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
-  return stream_step_impl(plan, model, chunk, S, hx, ola, reinterpret_cast<const float2*>(init_angles), seed, n_iter, momentum,
+  return stream_step_impl(plan, model, chunk, S, hx, ola, reinterpret_cast<const float2*>(init_angles), seed, d_seed, n_iter, momentum,
                           conv_mode, out, workspace, workspace_bytes, ST(stream));
 }
 

@@ -266,6 +266,7 @@ struct GlInitArgs {
   const float2* rtw;
   const float* winn;
   unsigned long long seed;
+  const unsigned long long* seed_ptr;
 };
 
 template <int WARPS>
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
     const int c = t - tb;
     float2 v[16];
     const unsigned long long base = ((unsigned long long)b * T + t) * (M + 1);
+    const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     mbar_wait(bar, c & 1);
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
@@ -318,13 +320,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
       float2& V = v[2 * (7 - rr) + 1];
       const float2 one = make_float2(1.f, 0.f);
       if (rr == 0 && lane == 0) {
-        const float2 a0 = a.seed ? rand_angle(a.seed, base) : one, aM = a.seed ? rand_angle(a.seed, base + M) : one;
-        const float2 a256 = a.seed ? rand_angle(a.seed, base + 256) : one;
+        const float2 a0 = seed ? rand_angle(seed, base) : one, aM = seed ? rand_angle(seed, base + M) : one;
+        const float2 a256 = seed ? rand_angle(seed, base + 256) : one;
         const float y0 = mg_s[0] * a0.x, yM = mg_s[M] * aM.x, m256 = mg_s[256];
         U = make_float2(y0 + yM, y0 - yM);
         V = make_float2(2.0f * m256 * a256.x, -2.0f * m256 * a256.y);
       } else {
-        const float2 ak = a.seed ? rand_angle(a.seed, base + k) : one, amk = a.seed ? rand_angle(a.seed, base + (M - k)) : one;
+        const float2 ak = seed ? rand_angle(seed, base + k) : one, amk = seed ? rand_angle(seed, base + (M - k)) : one;
         const float mk = mg_s[k], mmk = mg_s[M - k];
         irfft_merge(make_float2(mk * ak.x, mk * ak.y), make_float2(mmk * amk.x, mmk * amk.y), RT[k], U, V);
       }
@@ -356,10 +358,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
 }
 
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
-                           cudaStream_t st) {
+                           const unsigned long long* seed_ptr, cudaStream_t st) {
   GlInitArgs a;
   a.mag_tf = mag_tf; a.xout = xout; a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
-  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed;
+  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
   constexpr int W = 8;
   const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
   B2D_CUDA(cudaFuncSetAttribute(gl_fast512_init_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

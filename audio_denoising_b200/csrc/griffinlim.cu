@@ -39,6 +39,7 @@ struct GlArgs {
   float mom;
   int init, use_prev, store_prev;
   unsigned long long seed;  // init only: angles0 == null and seed != 0 -> in-kernel uniform draws
+  const unsigned long long* seed_ptr;  // optional device-resident seed (CUDA-graph replays change it without re-capture)
 };
 
 // normalised interior hop-block sample, 1 <= j <= T-1
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
   __syncthreads();
   const int half = M / 2 + 1;
   float* xo = a.xout + (size_t)(b * R + r) * (n + 1) * hop;
+  const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
 
   for (int tb = tbeg; tb < tend; tb += G) {
     const int gv = min(G, tend - tb);
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
             const float2 amk = a.angles0[((size_t)b * a.F + (M - k)) * T + t];
             yk = make_float2(yk.x * ak.x, yk.x * ak.y);
             ymk = make_float2(ymk.x * amk.x, ymk.x * amk.y);
-          } else if (a.seed) {
+          } else if (seed) {
             const unsigned long long base = ((unsigned long long)b * T + t) * (M + 1);
-            const float2 ak = rand_angle(a.seed, base + k), amk = rand_angle(a.seed, base + (M - k));
+            const float2 ak = rand_angle(seed, base + k), amk = rand_angle(seed, base + (M - k));
             yk = make_float2(yk.x * ak.x, yk.x * ak.y);
             ymk = make_float2(ymk.x * amk.x, ymk.x * amk.y);
           }
@@ -213,7 +215,7 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
 int gl_fast_warps_per_sm();
 bool gl_fast_persistent();
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
-                           cudaStream_t st);
+                           const unsigned long long* seed_ptr, cudaStream_t st);
 
 GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   GlPartition q;
@@ -274,7 +276,8 @@ size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
 }
 
 int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, unsigned long long seed, int B, int T, int n_iter,
-           float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st) {
+           float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st,
+           const unsigned long long* seed_ptr) {
   B2D_REQUIRE(p->hop * 2 == p->n_fft, B2D_ERR_UNSUPPORTED, "Griffin-Lim requires hop == n_fft/2 (got n_fft=%d hop=%d)", p->n_fft, p->hop);
   B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
   B2D_REQUIRE(momentum >= 0.f && momentum < 1.f, B2D_ERR_BAD_ARG, "momentum must be in range [0, 1). Found: %g", (double)momentum);
@@ -298,9 +301,9 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(q.R, B);
   // x_0 = istft(mag * angles_0)
-  a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed;
+  a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
   if (q.fast && init_angles == nullptr) {
-    int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, st);
+    int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
     if (rc != B2D_OK) return rc;
   } else {
     gl_generic_kernel<<<grid, 256, smem, st>>>(a);

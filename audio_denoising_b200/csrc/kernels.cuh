@@ -25,7 +25,8 @@ struct GlPartition {
 GlPartition gl_partition(const b2d_plan* p, int B, int T);
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy);
 int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, unsigned long long seed, int B, int T, int n_iter,
-           float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st);
+           float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st,
+           const unsigned long long* seed_ptr = nullptr);
 
 // model.cu
 size_t model_workspace_bytes(const b2d_model* m, int B, int T);

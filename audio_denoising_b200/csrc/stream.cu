@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) stream_ola_kernel(const float* __restrict
 }
 
 int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
-                     const float2* init_angles, unsigned long long seed, int n_iter, float momentum, int conv_mode, float* out,
-                     void* ws, size_t ws_bytes, cudaStream_t st) {
+                     const float2* init_angles, unsigned long long seed, const unsigned long long* d_seed, int n_iter, float momentum,
+                     int conv_mode, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
   B2D_REQUIRE(S >= 1 && S <= 65535, B2D_ERR_BAD_ARG, "sessions must be in [1, 65535] (got %d)", S);
   B2D_REQUIRE(p->hop * 2 == p->n_fft, B2D_ERR_UNSUPPORTED, "streaming requires hop == n_fft/2");
   B2D_REQUIRE(m->n_mels == p->n_mels, B2D_ERR_BAD_ARG, "plan n_mels (%d) != model n_mels (%d)", p->n_mels, m->n_mels);
@@ -96,7 +96,7 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
   } else if ((rc = launch_inverse_mel(p, w.mel, S, T, w.mag, false, st))) {
     return rc;
   }
-  if ((rc = gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st))) return rc;
+  if ((rc = gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st, d_seed))) return rc;
   stream_ola_kernel<<<S, 256, 0, st>>>(w.y, ola, out, p->hop);
   B2D_LAUNCH_CHECK("stream_ola_kernel");
   return B2D_OK;

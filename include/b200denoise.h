@@ -164,11 +164,13 @@ int b2d_denoise_noisy_phase(const b2d_plan* plan, const b2d_model* model, const 
 /* ---- streaming hop, app3.py:178-226 (one `while` iteration for S independent sessions) ----------
  * chunk [S, n_fft] raw float samples (the current input window), hx [S, hidden, bins] in/out,
  * ola [S, n_fft] in/out output overlap-add ring, out [S, hop] the hop of audio emitted by this step.
- * init_angles [S, F, 3] or NULL (then seed as for b2d_griffinlim).  compat != 0 keeps quirks Q2-Q4 of SURVEY.md Appendix C. */
+ * init_angles [S, F, 3] or NULL (then seed as for b2d_griffinlim; if d_seed != NULL the seed is read from that device
+ * word at run time instead, so a captured CUDA graph of this call can be replayed with a fresh seed per hop).
+ * Quirks Q2-Q4 of SURVEY.md Appendix C are kept. */
 size_t b2d_stream_step_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int S);
 int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* chunk, int S, float* hx,
-                    float* ola, const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum,
-                    int conv_mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
+                    float* ola, const b2d_c64* init_angles, unsigned long long seed, const unsigned long long* d_seed,
+                    int n_iter, float momentum, int conv_mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library has launched from the calling process (all threads); bench.py
  * reports the difference across the timed region as "gpu_launches". */
