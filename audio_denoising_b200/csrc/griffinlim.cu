@@ -40,10 +40,16 @@ struct GlArgs {
   int init, use_prev, store_prev;
   unsigned long long seed;  // init only: angles0 == null and seed != 0 -> in-kernel uniform draws
   const unsigned long long* seed_ptr;  // optional device-resident seed (CUDA-graph replays change it without re-capture)
+  // fused mode (R == 1, short clips): the init and all n_iter iterations in ONE launch, ping-ponging xa / xb
+  int fused_iters;  // -1: one step per launch (flags above); >= 0: run init + this many iterations here
+  float* xa;
+  float* xb;
 };
 
 // normalised interior hop-block sample, 1 <= j <= T-1
-__device__ __forceinline__ float x_block_sample(const float* __restrict__ part, const float* __restrict__ inv_env,
+// (`part` is deliberately not __restrict__: in fused mode the same launch wrote it one step earlier, so the loads must
+//  stay on the coherent path rather than ld.global.nc)
+__device__ __forceinline__ float x_block_sample(const float* part, const float* __restrict__ inv_env,
                                                 int b, int R, int n, int hop, int j, int i) {
   const int r1 = (j - 1) / n, r2 = j / n;
   float v = part[((size_t)(b * R + r1) * (n + 1) + (j - r1 * n)) * hop + i];
@@ -51,7 +57,7 @@ __device__ __forceinline__ float x_block_sample(const float* __restrict__ part, 
   return v * inv_env[i];
 }
 // sample i of padded hop-block j (0 <= j <= T) of the reflect-padded iterate
-__device__ __forceinline__ float x_padded(const float* __restrict__ part, const float* __restrict__ inv_env, int b,
+__device__ __forceinline__ float x_padded(const float* part, const float* __restrict__ inv_env, int b,
                                           int R, int n, int hop, int T, int j, int i) {
   if (j == 0) return (i == 0) ? x_block_sample(part, inv_env, b, R, n, hop, 2, 0)
                               : x_block_sample(part, inv_env, b, R, n, hop, 1, hop - i);
@@ -81,13 +87,30 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
   for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = 0.f;
   __syncthreads();
   const int half = M / 2 + 1;
-  float* xo = a.xout + (size_t)(b * R + r) * (n + 1) * hop;
   const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+  const int last_step = a.fused_iters >= 0 ? a.fused_iters : 0;
+  const float* cur_in = a.xin;
+  float* cur_out = a.xout;
+#pragma unroll 1
+  for (int step = 0; step <= last_step; ++step) {
+  // per-step flags: one step per launch takes them from the arguments; fused mode derives them (step 0 = init)
+  int f_init = a.init, f_use_prev = a.use_prev, f_store_prev = a.store_prev;
+  if (a.fused_iters >= 0) {
+    const int it = step - 1;
+    f_init = (step == 0);
+    f_use_prev = (it > 0 && a.mom != 0.f);
+    f_store_prev = (it + 1 < a.fused_iters && a.mom != 0.f);
+    cur_in = (step & 1) ? a.xa : a.xb;   // step 0 writes xa, step 1 reads xa writes xb, ...
+    cur_out = (step & 1) ? a.xb : a.xa;
+    for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = 0.f;
+    __syncthreads();
+  }
+  float* xo = cur_out + (size_t)(b * R + r) * (n + 1) * hop;
 
   for (int tb = tbeg; tb < tend; tb += G) {
     const int gv = min(G, tend - tb);
     float2 *src, *other;
-    if (!a.init) {
+    if (!f_init) {
       int first = 0;
       if (tb != tbeg) {
         for (int i = threadIdx.x; i < hop; i += blockDim.x) xin_s[i] = xin_s[G * hop + i];
@@ -96,7 +119,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       }
       for (int idx = threadIdx.x; idx < (gv + 1 - first) * hop; idx += blockDim.x) {
         const int c = first + idx / hop, i = idx % hop;
-        xin_s[c * hop + i] = x_padded(a.xin, a.inv_env, b, R, n, hop, T, tb + c, i);
+        xin_s[c * hop + i] = x_padded(cur_in, a.inv_env, b, R, n, hop, T, tb + c, i);
       }
       __syncthreads();
       for (int idx = threadIdx.x; idx < G * M; idx += blockDim.x) {
@@ -124,17 +147,17 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
         float2 yk, ymk;
         if (k == 0) {
           float a0 = xk.x, aM = xmk.x;
-          if (a.use_prev) {
+          if (f_use_prev) {
             const float2 pv = tp[0];
             a0 -= a.mom * pv.x;
             aM -= a.mom * pv.y;
           }
           yk = make_float2(mk * (a0 / (fabsf(a0) + 1e-16f)), 0.f);
           ymk = make_float2(mmk * (aM / (fabsf(aM) + 1e-16f)), 0.f);
-          if (a.store_prev) tp[0] = make_float2(xk.x, xmk.x);
+          if (f_store_prev) tp[0] = make_float2(xk.x, xmk.x);
         } else {
           float2 ak = xk, amk = xmk;
-          if (a.use_prev) {
+          if (f_use_prev) {
             const float2 pk = tp[k], pmk = tp[M - k];
             ak = make_float2(xk.x - a.mom * pk.x, xk.y - a.mom * pk.y);
             amk = make_float2(xmk.x - a.mom * pmk.x, xmk.y - a.mom * pmk.y);
@@ -142,7 +165,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
           const float2 uk = unit_dir(ak), umk = unit_dir(amk);
           yk = make_float2(mk * uk.x, mk * uk.y);
           ymk = make_float2(mmk * umk.x, mmk * umk.y);
-          if (a.store_prev) {
+          if (f_store_prev) {
             tp[k] = xk;
             if (2 * k != M) tp[M - k] = xmk;
           }
@@ -196,6 +219,8 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
     __syncthreads();
   }
   for (int i = threadIdx.x; i < hop; i += blockDim.x) xo[(size_t)(tend - tbeg) * hop + i] = carry_s[i];
+  __syncthreads();  // fused mode: this CTA's global writes are visible to all its threads before the next step reads them
+  }  // step
 }
 
 // partial hop-block format -> [B, hop*(T-1)] waveform (envelope-normalised, optional per-clip scale)
@@ -300,6 +325,17 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * q.G * p->M) + sizeof(float) * (size_t)((q.G + 2) * p->hop) + 16;
   B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(q.R, B);
+  a.fused_iters = -1; a.xa = xa; a.xb = xb;
+  float* cur = xa;
+  float* nxt = xb;
+  if (!q.fast && q.R == 1 && T <= 16 && getenv("B2D_GL_NO_FUSE") == nullptr) {
+    // short clips (streaming hops: T = 3): every dependency stays inside one CTA -> init + all iterations in one launch
+    a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
+    a.fused_iters = n_iter;
+    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+    B2D_LAUNCH_CHECK("gl_generic_kernel(fused)");
+    cur = (n_iter & 1) ? xb : xa;  // step s writes xa when s is even; the last step is s = n_iter
+  } else {
   // x_0 = istft(mag * angles_0)
   a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
   if (q.fast && init_angles == nullptr) {
@@ -309,8 +345,6 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     gl_generic_kernel<<<grid, 256, smem, st>>>(a);
     B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
   }
-  float* cur = xa;
-  float* nxt = xb;
   a.init = 0; a.angles0 = nullptr;
   for (int it = 0; it < n_iter; ++it) {
     a.use_prev = (it > 0 && a.mom != 0.f) ? 1 : 0;
@@ -324,6 +358,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
       B2D_LAUNCH_CHECK("gl_generic_kernel");
     }
     float* t = cur; cur = nxt; nxt = t;
+  }
   }
   gl_stitch_kernel<<<dim3(T - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop);
   B2D_LAUNCH_CHECK("gl_stitch_kernel");
