@@ -178,6 +178,7 @@ void b2d_model_destroy(b2d_model* m) {
   if (!m) return;
   cudaFree(m->d_blob);
   cudaFree(m->d_tc);
+  free(m->h_blob);
   delete m;
 }
 int b2d_model_n_mels(const b2d_model* m) { return m ? m->n_mels : B2D_ERR_BAD_ARG; }

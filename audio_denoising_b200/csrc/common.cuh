@@ -76,6 +76,7 @@ struct b2d_model {
   int n_mels;
   int device;
   float* d_blob;      // all packed tensors, one allocation
+  float* h_blob;      // host copy of the same (weights passed by value as __grid_constant__ kernel parameters)
   size_t blob_floats;
   // offsets (in floats) into d_blob, see model.cu
   int enc_w[6], enc_pb[6];

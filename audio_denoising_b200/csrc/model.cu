@@ -11,6 +11,7 @@
 // the tcgen05 implicit-GEMM variants of the encoder / decoder.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "kernels.cuh"
@@ -439,6 +440,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decoder_kernel(const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// (Measured dead end, kept as a note: passing the 27.5 KB decoder weights as a __grid_constant__ kernel parameter so that
+//  FMAs take warp-uniform constant operands was slower -- register-indexed LDC.64 when partially unrolled (+0.4 ms), and
+//  110 KB of straight-line code when fully unrolled (+0.05 ms).  These kernels are bound by the shared-memory -> register
+//  path: a broadcast float4 weight load still moves 512 B to the register file.)
 // decoder, register-tiled: a warp works on FW = 2 frames at once; a lane owns one INPUT position j of one
 // frame and computes all output channels of both outputs 2j and 2j+1 (2 x 17 accumulators in registers).
 // Per input channel: 2 activation loads, 15 broadcast float4 weight loads, 60 FMAs.
@@ -700,6 +705,8 @@ int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
     }
   }
   m->blob_floats = blob.size();
+  m->h_blob = static_cast<float*>(malloc(blob.size() * sizeof(float)));  // host copy: constant-bank kernels take weights by value
+  if (m->h_blob) memcpy(m->h_blob, blob.data(), blob.size() * sizeof(float));
   B2D_CUDA(cudaMalloc(&m->d_blob, blob.size() * sizeof(float)));
   B2D_CUDA(cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   return model_pack_tc_weights(m, hp);  // TF32 big/small weight images for the tcgen05 path (conv_tc.cu)
