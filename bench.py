@@ -316,6 +316,17 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * SECONDS / float(t2.item())
+    # host link bandwidth seen by this process (explains e2e when the PCIe link, not the kernels, is the limit)
+    def copy_gbs(dst, src):
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return round(3 * src.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+    link = {"h2d_gbs": copy_gbs(noisy, noisy_host), "d2h_gbs": copy_gbs(host_out[0], wave)}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -336,7 +347,7 @@ def run_b200(args):
                        "l2": "per-step working set ~0.6 GB >> 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * Lout * 4,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "pipelined": True, **link},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
