@@ -93,6 +93,11 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
     const double a = -2.0 * M_PI * (double)k / (double)N;
     rtw[k] = make_float2((float)cos(a), (float)sin(a));
   }
+  std::vector<float2> tw512(512);
+  for (int k = 0; k < 512; ++k) {
+    const double a = -2.0 * M_PI * (double)k / 512.0;
+    tw512[k] = make_float2((float)cos(a), (float)sin(a));
+  }
   std::vector<float> win(N), winn(N), inv_env(hop);
   for (int n = 0; n < N; ++n) {
     // torch.hann_window(N, periodic=True) evaluated in float32 like torch does (0.5 - 0.5 cos)
@@ -124,7 +129,7 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
   std::vector<float> pinv((size_t)p->Fp * n_mels, 0.f);
   memcpy(pinv.data(), h_pinv, sizeof(float) * (size_t)F * n_mels);
   int rc;
-  if ((rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_rtw, rtw)) || (rc = upload(&p->d_win, win)) ||
+  if ((rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw512, tw512)) || (rc = upload(&p->d_rtw, rtw)) || (rc = upload(&p->d_win, win)) ||
       (rc = upload(&p->d_winn, winn)) || (rc = upload(&p->d_inv_env, inv_env)) || (rc = upload(&p->d_mel_lo, lo)) ||
       (rc = upload(&p->d_mel_cnt, cnt)) || (rc = upload(&p->d_mel_off, off)) || (rc = upload(&p->d_mel_w, mw)) ||
       (rc = upload(&p->d_pinv, pinv))) {
@@ -141,7 +146,7 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
 
 void b2d_plan_destroy(b2d_plan* p) {
   if (!p) return;
-  cudaFree(p->d_tw); cudaFree(p->d_rtw); cudaFree(p->d_win); cudaFree(p->d_winn); cudaFree(p->d_inv_env);
+  cudaFree(p->d_tw); cudaFree(p->d_tw512); cudaFree(p->d_rtw); cudaFree(p->d_win); cudaFree(p->d_winn); cudaFree(p->d_inv_env);
   cudaFree(p->d_mel_lo); cudaFree(p->d_mel_cnt); cudaFree(p->d_mel_off); cudaFree(p->d_mel_w); cudaFree(p->d_pinv);
   cudaFree(p->d_tw8);
   delete p;

@@ -58,6 +58,7 @@ struct b2d_plan {
   int device;
   int num_sms;
   float2* d_tw;       // [M]      W_M^k   = exp(-2 pi i k / M)
+  float2* d_tw512;    // [512]    W_512^k (register FFT of the n_fft = 512 / 1024 fast paths)
   float2* d_rtw;      // [M]      W_N^k   = exp(-2 pi i k / N)   (real-FFT split twiddles)
   float* d_win;       // [N]      periodic Hann
   float* d_winn;      // [N]      Hann / N (synthesis window with the irfft 1/N folded in)

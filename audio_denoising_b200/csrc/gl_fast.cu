@@ -361,7 +361,7 @@ int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, 
                            const unsigned long long* seed_ptr, cudaStream_t st) {
   GlInitArgs a;
   a.mag_tf = mag_tf; a.xout = xout; a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
-  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
+  a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
   constexpr int W = 8;
   const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
   B2D_CUDA(cudaFuncSetAttribute(gl_fast512_init_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -489,7 +489,7 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
                         cudaStream_t st) {
   StftFastArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.n_mels = p->n_mels;
-  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win;
+  a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win;
   a.mel_lo = p->d_mel_lo; a.mel_cnt = p->d_mel_cnt; a.mel_off = p->d_mel_off; a.mel_w = p->d_mel_w; a.mel_nnz = p->mel_nnz;
   a.logmel_bt = logmel_bt;
   constexpr int W = 8;
@@ -535,7 +535,7 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
   GlFastArgs a;
   a.mag_tf = mag_tf; a.tprev = tprev; a.xin = xin; a.xout = xout;
   a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
-  a.tw512 = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev;
   const char* e = getenv("B2D_GL_VARIANT");
   const int variant = e ? atoi(e) : 4;  // default: persistent, 12 warps/SM, tprev / mag / iterate all staged by TMA

@@ -223,5 +223,37 @@ B2D_HD void special_update(float2& U, float2& V, float2 p0, float2 p256, float m
   V = make_float2(2.0f * m256 * u.x, -2.0f * m256 * u.y);
 }
 
+// ---- n_fft = 512: two consecutive real frames a, b ride one 512-point complex transform z = a + i b -----------------
+// For a pair slot holding Z[lo] (lo <= 256) and Z[hi = 512 - lo]:  2 A[lo] = Z[lo] + conj Z[hi],  2 B[lo] = -i (Z[lo] - conj Z[hi]).
+// Update both frames' bins (tprev holds 2 x rebuilt, as above) and rebuild Z'[lo] = Ya + i Yb, Z'[hi] = conj Ya + i conj Yb.
+B2D_HD void pair2_update(float2& Zlo, float2& Zhi, float2 pa, float2 pb, float ma, float mb, float mom, bool use_prev,
+                         float2& xa, float2& xb) {
+  xa = make_float2(Zlo.x + Zhi.x, Zlo.y - Zhi.y);
+  xb = make_float2(Zlo.y + Zhi.y, Zhi.x - Zlo.x);
+  float2 aa = xa, ab = xb;
+  if (use_prev) {
+    aa = make_float2(fmaf(-mom, pa.x, xa.x), fmaf(-mom, pa.y, xa.y));
+    ab = make_float2(fmaf(-mom, pb.x, xb.x), fmaf(-mom, pb.y, xb.y));
+  }
+  const float2 ua = unit_dir_fast(aa), ub = unit_dir_fast(ab);
+  const float2 ya = make_float2(ma * ua.x, ma * ua.y), yb = make_float2(mb * ub.x, mb * ub.y);
+  Zlo = make_float2(ya.x - yb.y, ya.y + yb.x);
+  Zhi = make_float2(ya.x + yb.y, yb.x - ya.y);
+}
+// lane 0, slot 0: U = Z[0] = (DC of a, DC of b), V = Z[256] = (Nyquist of a, Nyquist of b), all real.
+// p0a / p0b: packed (DC, Nyquist) of the previous rebuilt of frames a / b; returns the new packed values.
+B2D_HD void special2_update(float2& U, float2& V, float2 p0a, float2 p0b, float ma0, float maN, float mb0, float mbN, float mom,
+                            bool use_prev, float2& x0a, float2& x0b) {
+  x0a = make_float2(2.0f * U.x, 2.0f * V.x);
+  x0b = make_float2(2.0f * U.y, 2.0f * V.y);
+  float a0 = x0a.x, aN = x0a.y, b0 = x0b.x, bN = x0b.y;
+  if (use_prev) {
+    a0 = fmaf(-mom, p0a.x, a0); aN = fmaf(-mom, p0a.y, aN);
+    b0 = fmaf(-mom, p0b.x, b0); bN = fmaf(-mom, p0b.y, bN);
+  }
+  U = make_float2(ma0 * (a0 * inv_norm(a0 * a0)), mb0 * (b0 * inv_norm(b0 * b0)));
+  V = make_float2(maN * (aN * inv_norm(aN * aN)), mbN * (bN * inv_norm(bN * bN)));
+}
+
 }  // namespace fast512
 }  // namespace b2d

@@ -239,34 +239,42 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, con
                       int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast.cu
 int gl_fast_warps_per_sm();
 bool gl_fast_persistent();
+int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
+                        int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast_n512.cu
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            const unsigned long long* seed_ptr, cudaStream_t st);
 
 GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   GlPartition q;
   q.G = (p->M <= 1024) ? 4 : 2;
-  q.fast = (p->n_fft == 1024 && p->hop == 512 && getenv("B2D_GL_GENERIC") == nullptr);
+  q.fast = 0;
+  if (getenv("B2D_GL_GENERIC") == nullptr) {
+    if (p->n_fft == 1024 && p->hop == 512) q.fast = 1;
+    if (p->n_fft == 512 && p->hop == 256) q.fast = 2;
+  }
   if (q.fast) {
     // one warp per run.  Pick the number of runs per clip R that minimises the busiest SM's load
     // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
     const int wps = gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
     const int maxR = (T + 3) / 4;  // at least 4 frames per run
-    if (gl_fast_persistent()) {
+    if (gl_fast_persistent() || q.fast == 2) {
       // Measured: a warp needs ~4.5 us per frame whether 1 or 12 warps share the SM (the kernel is latency-bound per
       // warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).  Minimise that; ties -> longer runs
       // (less boundary traffic).
       long best = -1; int bestR = 1;
+      int bestN = T;
       for (int R = 1; R <= maxR; ++R) {
-        const int n = (T + R - 1) / R;
+        int n = (T + R - 1) / R;
+        if (q.fast == 2) n = (n + 1) & ~1;  // n_fft 512 walks a run two frames at a time
         const int Reff = (T + n - 1) / n;
         const long runs = (long)B * Reff;
         const long rounds = (runs + slots - 1) / slots;
-        const long cost = rounds * n;
-        if (best < 0 || cost < best) { best = cost; bestR = Reff; }
+        const long cost = rounds * (q.fast == 2 ? n / 2 : n);
+        if (best < 0 || cost < best) { best = cost; bestR = Reff; bestN = n; }
       }
-      q.n = (T + bestR - 1) / bestR;
-      q.R = (T + q.n - 1) / q.n;
+      q.n = bestN;
+      q.R = bestR;
       return q;
     }
     int R = (int)(slots / B);
@@ -338,7 +346,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   } else {
   // x_0 = istft(mag * angles_0)
   a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
-  if (q.fast && init_angles == nullptr) {
+  if (q.fast == 1 && init_angles == nullptr) {
     int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
     if (rc != B2D_OK) return rc;
   } else {
@@ -350,8 +358,11 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     a.use_prev = (it > 0 && a.mom != 0.f) ? 1 : 0;
     a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
     a.xin = cur; a.xout = nxt;
-    if (q.fast) {
+    if (q.fast == 1) {
       int rc = launch_gl_fast512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
+      if (rc != B2D_OK) return rc;
+    } else if (q.fast == 2) {
+      int rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
       if (rc != B2D_OK) return rc;
     } else {
       gl_generic_kernel<<<grid, 256, smem, st>>>(a);

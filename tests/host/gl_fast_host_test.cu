@@ -117,6 +117,78 @@ int main() {
     nrm += pow(yref[2 * m], 2) + pow(yref[2 * m + 1], 2);
   }
   printf("frame iteration rel err %.3e\n", sqrt(e / nrm)); if (sqrt(e / nrm) > 5e-6) bad++;
+  // ---- n_fft = 512: two real frames in one complex transform -------------------------------------------------------
+  {
+    const int N2 = 512, H2 = 256;
+    std::vector<float> fa(N2), fb(N2);
+    for (auto& q : fa) q = frand(seed);
+    for (auto& q : fb) q = frand(seed);
+    std::vector<float2> Pa(H2), Pb(H2);  // 2 x previous rebuilt, slot 0 packed (DC, Nyquist)
+    std::vector<float> ma(H2 + 4), mb(H2 + 4);
+    for (int k = 0; k < H2; ++k) { Pa[k] = make_float2(10 * frand(seed), 10 * frand(seed)); Pb[k] = make_float2(10 * frand(seed), 10 * frand(seed)); }
+    for (int k = 0; k <= H2; ++k) { ma[k] = 2.0f * (frand(seed) + 0.6f); mb[k] = 2.0f * (frand(seed) + 0.6f); }
+    auto ref = [&](const std::vector<float>& f, const std::vector<float2>& P, const std::vector<float>& mg, std::vector<double>& y, std::vector<cd>& X2) {
+      std::vector<cd> X(H2 + 1), Y(H2 + 1);
+      for (int k = 0; k <= H2; ++k) { cd a = 0; for (int n = 0; n < N2; ++n) a += (double)f[n] * std::polar(1.0, -2 * M_PI * (double)((long)n * k % N2) / N2); X[k] = a; }
+      X2.resize(H2 + 1);
+      for (int k = 0; k <= H2; ++k) {
+        cd p = (k == 0) ? cd(P[0].x, 0) : (k == H2) ? cd(P[0].y, 0) : cd(P[k].x, P[k].y);
+        cd a = 2.0 * X[k] - (double)mom * p;
+        if (k == 0 || k == H2) a = cd(a.real(), 0);
+        Y[k] = (double)mg[k] * a / (std::abs(a) + 1e-16);
+        X2[k] = 2.0 * X[k];
+      }
+      y.resize(N2);
+      for (int n = 0; n < N2; ++n) {
+        cd a = Y[0].real() + Y[H2].real() * ((n & 1) ? -1.0 : 1.0);
+        for (int k = 1; k < H2; ++k) a += 2.0 * (Y[k] * std::polar(1.0, 2 * M_PI * (double)((long)n * k % N2) / N2)).real();
+        y[n] = a.real();
+      }
+    };
+    std::vector<double> ya, yb; std::vector<cd> Xa2, Xb2;
+    ref(fa, Pa, ma, ya, Xa2); ref(fb, Pb, mb, yb, Xb2);
+    for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) v[l][q] = make_float2(fa[l + 32 * q], fb[l + 32 * q]);
+    forward();
+    std::vector<float2> nPa(H2, make_float2(0, 0)), nPb(H2, make_float2(0, 0));
+    std::vector<int> st2(H2, 0);
+    for (int l = 0; l < 32; ++l) {
+      if (l == 0) lane0_permute(v[l]);
+      for (int r = 0; r < 8; ++r) {
+        const int kU = slot_k(l, r);
+        float2& U = v[l][2 * r];
+        float2& V = v[l][2 * (7 - r) + 1];
+        if (l == 0 && r == 0) {
+          float2 x0a, x0b;
+          special2_update(U, V, Pa[0], Pb[0], ma[0], ma[H2], mb[0], mb[H2], mom, true, x0a, x0b);
+          nPa[0] = x0a; nPb[0] = x0b; st2[0]++;
+        } else {
+          const bool swap = (kU > H2);
+          const int kb = swap ? N2 - kU : kU;
+          float2 xa, xb;
+          if (swap) pair2_update(V, U, Pa[kb], Pb[kb], ma[kb], mb[kb], mom, true, xa, xb);
+          else pair2_update(U, V, Pa[kb], Pb[kb], ma[kb], mb[kb], mom, true, xa, xb);
+          nPa[kb] = xa; nPb[kb] = xb; st2[kb]++;
+        }
+      }
+      if (l == 0) lane0_unpermute(v[l]);
+    }
+    for (int k = 0; k < H2; ++k) if (st2[k] != 1) { printf("n_fft512: bin %d handled %d times\n", k, st2[k]); bad++; }
+    double e1 = 0, n1 = 0;
+    for (int k = 1; k < H2; ++k) {
+      e1 += std::norm(cd(nPa[k].x, nPa[k].y) - Xa2[k]) + std::norm(cd(nPb[k].x, nPb[k].y) - Xb2[k]);
+      n1 += std::norm(Xa2[k]) + std::norm(Xb2[k]);
+    }
+    e1 += std::norm(cd(nPa[0].x, 0) - Xa2[0]) + std::norm(cd(nPa[0].y, 0) - Xa2[H2]) + std::norm(cd(nPb[0].x, 0) - Xb2[0]) + std::norm(cd(nPb[0].y, 0) - Xb2[H2]);
+    printf("n_fft512 rebuilt rel err %.3e\n", sqrt(e1 / n1)); if (sqrt(e1 / n1) > 2e-6) bad++;
+    inverse();
+    double e2 = 0, n2 = 0;
+    for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) {
+      const int m = l + 32 * q;
+      e2 += pow(v[l][q].x - ya[m], 2) + pow(v[l][q].y - yb[m], 2);
+      n2 += pow(ya[m], 2) + pow(yb[m], 2);
+    }
+    printf("n_fft512 frame-pair iteration rel err %.3e\n", sqrt(e2 / n2)); if (sqrt(e2 / n2) > 5e-6) bad++;
+  }
   printf(bad ? "FAIL\n" : "OK\n");
   return bad;
 }
