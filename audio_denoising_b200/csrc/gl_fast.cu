@@ -21,6 +21,9 @@ struct GlFastArgs {
   const float* inv_env;  // [512]
   float mom;
   int use_prev, store_prev;
+  // last iteration only: hop-blocks interior to a run are final -> written straight to the waveform
+  float* wave;             // [B, HOP*(T-1)] or null
+  const float* out_scale;  // [B] or null
 };
 
 // ---- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX) ------------------------------------------
@@ -239,12 +242,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
     __syncwarp();
     inv3_load(lane, v, tw, S);
     // ---- synthesis window + overlap-add: block c = carry + first half ; carry = second half --------------
-    float2* dst = reinterpret_cast<float2*>(xo + (size_t)c * HOP);
+    if (a.wave != nullptr && c >= 1) {
+      // last iteration, block interior to this run: both contributions are here, so this is the final sample --
+      // divide by the window envelope, apply the clip's scale and write the waveform directly (skips the stitch)
+      const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
+      float2* wdst = reinterpret_cast<float2*>(a.wave + (size_t)b * HOP * (T - 1) + (size_t)(t - 1) * HOP);
+      const float2* ie = reinterpret_cast<const float2*>(a.inv_env);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
-      dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
-      carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+      for (int q = 0; q < 8; ++q) {
+        const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
+        const float2 e = ie[lane + 32 * q];
+        wdst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x) * e.x * sc, fmaf(v[q].y, w0.y, carry[q].y) * e.y * sc);
+        carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+      }
+    } else {
+      float2* dst = reinterpret_cast<float2*>(xo + (size_t)c * HOP);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
+        dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
+        carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+      }
     }
   }
   float2* dst = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
@@ -531,12 +549,12 @@ bool gl_fast_persistent() {
 }
 
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
-                      int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st) {
+                      int n, int R, float mom, int use_prev, int store_prev, float* wave, const float* out_scale, cudaStream_t st) {
   GlFastArgs a;
   a.mag_tf = mag_tf; a.tprev = tprev; a.xin = xin; a.xout = xout;
   a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
-  a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev;
+  a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev; a.wave = wave; a.out_scale = out_scale;
   const char* e = getenv("B2D_GL_VARIANT");
   const int variant = e ? atoi(e) : 4;  // default: persistent, 12 warps/SM, tprev / mag / iterate all staged by TMA
   if (variant == 1) return launch_variant<4, 3, false, false>(a, p->num_sms, st);   // 12 warps/SM, up to 168 registers

@@ -226,9 +226,10 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
 // partial hop-block format -> [B, hop*(T-1)] waveform (envelope-normalised, optional per-clip scale)
 __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict__ part, const float* __restrict__ inv_env,
                                                         const float* __restrict__ out_scale, float* __restrict__ wave,
-                                                        int T, int n, int R, int hop) {
+                                                        int T, int n, int R, int hop, int jstep) {
   const int b = blockIdx.y;
-  const int j = blockIdx.x + 1;  // hop-block 1..T-1
+  const int j = (blockIdx.x + 1) * jstep;  // hop-block 1..T-1 (jstep = 1) or the run boundaries n, 2n, ... (jstep = n)
+  if (j > T - 1) return;
   const float sc = out_scale ? out_scale[b] : 1.0f;
   float* dst = wave + (size_t)b * hop * (T - 1) + (size_t)(j - 1) * hop;
   for (int i = threadIdx.x; i < hop; i += blockDim.x) dst[i] = x_block_sample(part, inv_env, b, R, n, hop, j, i) * sc;
@@ -236,7 +237,8 @@ __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
-                      int n, int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast.cu
+                      int n, int R, float mom, int use_prev, int store_prev, float* wave, const float* out_scale,
+                      cudaStream_t st);  // gl_fast.cu
 int gl_fast_warps_per_sm();
 bool gl_fast_persistent();
 int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
@@ -336,6 +338,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   a.fused_iters = -1; a.xa = xa; a.xb = xb;
   float* cur = xa;
   float* nxt = xb;
+  bool direct_interior = false;
   if (!q.fast && q.R == 1 && T <= 16 && getenv("B2D_GL_NO_FUSE") == nullptr) {
     // short clips (streaming hops: T = 3): every dependency stays inside one CTA -> init + all iterations in one launch
     a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
@@ -359,8 +362,11 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
     a.xin = cur; a.xout = nxt;
     if (q.fast == 1) {
-      int rc = launch_gl_fast512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
+      const bool last = (it + 1 == n_iter) && getenv("B2D_GL_NO_DIRECT") == nullptr;  // last iteration: run-interior hop-blocks go straight to `wave`
+      int rc = launch_gl_fast512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev,
+                                 last ? wave : nullptr, out_scale, st);
       if (rc != B2D_OK) return rc;
+      direct_interior = last;
     } else if (q.fast == 2) {
       int rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
       if (rc != B2D_OK) return rc;
@@ -371,8 +377,16 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     float* t = cur; cur = nxt; nxt = t;
   }
   }
-  gl_stitch_kernel<<<dim3(T - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop);
-  B2D_LAUNCH_CHECK("gl_stitch_kernel");
+  if (direct_interior) {
+    // only the hop-blocks on run boundaries (j = r * n, r = 1 .. R-1) still need the sum of two partial slots
+    if (q.R > 1) {
+      gl_stitch_kernel<<<dim3(q.R - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop, q.n);
+      B2D_LAUNCH_CHECK("gl_stitch_kernel(boundaries)");
+    }
+  } else {
+    gl_stitch_kernel<<<dim3(T - 1, B), 256, 0, st>>>(cur, p->d_inv_env, out_scale, wave, T, q.n, q.R, p->hop, 1);
+    B2D_LAUNCH_CHECK("gl_stitch_kernel");
+  }
   return B2D_OK;
 }
 
