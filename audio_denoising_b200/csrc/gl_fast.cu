@@ -406,13 +406,19 @@ struct StftFastArgs {
   float* logmel_bt;
 };
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) stft_fast512_kernel(const StftFastArgs a) {
+// One warp per frame; the frame's 4 KB of samples arrive by TMA bulk copy into a two-slot per-warp ring one frame
+// ahead (interior frames are contiguous in the clip); the two reflect-padded frames at the clip edges are staged
+// by the warp itself.
+constexpr int STFT_WARPS = 16;
+constexpr int STFT_WSMEM = XCH * 8 + 2 * N * 4 + 16;  // exchange | two frame buffers | two mbarriers
+
+__global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const StftFastArgs a) {
+  constexpr int WARPS = STFT_WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* WIN = reinterpret_cast<float2*>(smem_raw);  // [512] plain window pairs
   float2* RT = WIN + 512;
   float* melw = reinterpret_cast<float*>(RT + 512);   // [mel_nnz rounded up to 4]
-  float2* xch_all = reinterpret_cast<float2*>(melw + ((a.mel_nnz + 3) & ~3));
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(melw + ((a.mel_nnz + 3) & ~3));
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     WIN[i] = make_float2(a.win[2 * i], a.win[2 * i + 1]);
     RT[i] = a.rtw[i];
@@ -420,50 +426,69 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft_fast512_kernel(const StftF
   for (int i = threadIdx.x; i < a.mel_nnz; i += blockDim.x) melw[i] = a.mel_w[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* S = xch_all + warp * XCH;
+  unsigned char* wsm = warp_base + (size_t)warp * STFT_WSMEM;
+  float2* S = reinterpret_cast<float2*>(wsm);
   float* Sf = reinterpret_cast<float*>(S);
+  float* fbuf = reinterpret_cast<float*>(wsm + XCH * 8);  // [2][1024]
+  uint64_t* fbar = reinterpret_cast<uint64_t*>(wsm + XCH * 8 + 2 * N * 4);
+  if (lane == 0) {
+    mbar_init(fbar, 1);
+    mbar_init(fbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   LaneTw tw;
   lane_twiddles(lane, a.tw512, tw);
   const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
   const size_t nframes = (size_t)a.B * a.T;
-  const bool even = (a.L & 1) == 0;
+  const size_t stride = (size_t)gridDim.x * WARPS;
+  const bool tma_ok = (a.L % 4) == 0;  // 16-byte aligned clip rows
+  // frame f is "interior" when its 1024 samples lie inside the clip: then it is one contiguous, aligned 4 KB read
+  auto interior = [&](size_t f, const float*& src) {
+    const int b = (int)(f / a.T), t = (int)(f - (size_t)b * a.T);
+    const long s0 = (long)t * HOP - HOP;
+    src = a.wave + (size_t)b * a.L + s0;
+    return tma_ok && s0 >= 0 && s0 + N <= a.L;
+  };
+  uint32_t use0 = 0, use1 = 0;
+  size_t f = (size_t)blockIdx.x * WARPS + warp;
+  int slot = 0;
+  if (f < nframes && lane == 0) {
+    const float* src;
+    if (interior(f, src)) { mbar_expect_tx(fbar, N * 4); bulk_g2s(fbuf, src, N * 4, fbar); }
+  }
 #pragma unroll 1
-  for (size_t f = (size_t)blockIdx.x * WARPS + warp; f < nframes; f += (size_t)gridDim.x * WARPS) {
+  for (; f < nframes; f += stride, slot ^= 1) {
     const int b = (int)(f / a.T), t = (int)(f - (size_t)b * a.T);
     const float* x = a.wave + (size_t)b * a.L;
     const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
-    const long s0 = (long)t * HOP - HOP;  // first sample of the frame in clip coordinates
-    {  // next frame of this warp -> L2 (4 KB = 32 lines)
-      const size_t fn = f + (size_t)gridDim.x * WARPS;
-      if (fn < nframes) {
-        const int bn = (int)(fn / a.T), tn = (int)(fn - (size_t)bn * a.T);
-        const long sn = (long)tn * HOP - HOP + lane * 32;
-        if (sn >= 0 && sn + 32 <= a.L) prefetch_l2(a.wave + (size_t)bn * a.L + sn);
+    float* cur = fbuf + slot * N;
+    const float* src_cur;
+    const bool cur_tma = interior(f, src_cur);
+    if (lane == 0 && f + stride < nframes) {  // next frame of this warp into the other slot
+      const float* src;
+      if (interior(f + stride, src)) { mbar_expect_tx(fbar + (slot ^ 1), N * 4); bulk_g2s(fbuf + (slot ^ 1) * N, src, N * 4, fbar + (slot ^ 1)); }
+    }
+    if (cur_tma) {
+      if (slot) { mbar_wait(fbar + 1, use1 & 1); ++use1; } else { mbar_wait(fbar, use0 & 1); ++use0; }
+    } else {  // reflect-padded edge frame (or unaligned clip length): stage it here
+      const long s0 = (long)t * HOP - HOP;
+      for (int i = lane; i < N; i += 32) {
+        long sidx = s0 + i;
+        if (sidx < 0) sidx = -sidx;
+        if (sidx >= a.L) sidx = 2L * (a.L - 1) - sidx;
+        cur[i] = (sidx >= 0 && sidx < a.L) ? x[sidx] : 0.f;
       }
+      __syncwarp();
     }
     float2 v[16];
-    if (even && s0 >= 0 && s0 + N <= a.L) {
-      const float2* src = reinterpret_cast<const float2*>(x + s0);
+    {
+      const float2* c2 = reinterpret_cast<const float2*>(cur);
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const float2 xv = src[lane + 32 * q];
+        const float2 xv = c2[lane + 32 * q];
         const float2 wv = WIN[lane + 32 * q];
         v[q] = make_float2((xv.x / sc) * wv.x, (xv.y / sc) * wv.y);
-      }
-    } else {  // reflect-padded edges (or odd L): stage through shared memory
-      __syncwarp();
-      for (int i = lane; i < N; i += 32) {
-        long s = s0 + i;
-        if (s < 0) s = -s;
-        if (s >= a.L) s = 2L * (a.L - 1) - s;
-        Sf[i] = (s >= 0 && s < a.L) ? x[s] / sc : 0.f;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float2 xv = S[lane + 32 * q];
-        const float2 wv = WIN[lane + 32 * q];
-        v[q] = make_float2(xv.x * wv.x, xv.y * wv.y);
       }
     }
     __syncwarp();
@@ -492,7 +517,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft_fast512_kernel(const StftF
       }
     }
     __syncwarp();
-    for (int m = lane; m < a.n_mels; m += 32) {
+    // mel bins are paired narrow + wide (m, n_mels-1-m) so the lanes' loop lengths are balanced
+    for (int mi = lane; mi < a.n_mels; mi += 32) {
+      const int m = (mi < a.n_mels / 2) ? mi : (a.n_mels - 1) - (mi - a.n_mels / 2);
       const int lo = a.mel_lo[m], cnt = a.mel_cnt[m];
       const float* w = melw + a.mel_off[m];
       float acc = 0.f;
@@ -510,13 +537,13 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win;
   a.mel_lo = p->d_mel_lo; a.mel_cnt = p->d_mel_cnt; a.mel_off = p->d_mel_off; a.mel_w = p->d_mel_w; a.mel_nnz = p->mel_nnz;
   a.logmel_bt = logmel_bt;
-  constexpr int W = 8;
-  const size_t smem = sizeof(float2) * 1024 + sizeof(float) * ((p->mel_nnz + 3) & ~3) + sizeof(float2) * (size_t)W * XCH;
-  B2D_CUDA(cudaFuncSetAttribute(stft_fast512_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int W = STFT_WARPS;
+  const size_t smem = sizeof(float2) * 1024 + sizeof(float) * ((p->mel_nnz + 3) & ~3) + (size_t)W * STFT_WSMEM;
+  B2D_CUDA(cudaFuncSetAttribute(stft_fast512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t nframes = (size_t)B * a.T;
   const size_t want = (nframes + W - 1) / W;
-  const int grid = (int)(want < (size_t)p->num_sms * 2 ? want : (size_t)p->num_sms * 2);
-  stft_fast512_kernel<W><<<grid, W * 32, smem, st>>>(a);
+  const int grid = (int)(want < (size_t)p->num_sms ? want : (size_t)p->num_sms);
+  stft_fast512_kernel<<<grid, W * 32, smem, st>>>(a);
   B2D_LAUNCH_CHECK("stft_fast512_kernel");
   return B2D_OK;
 }
