@@ -68,6 +68,12 @@ SIGNATURES = {
     "b2d_denoise_noisy_phase": (_i, [_vp, _vp, _vp, _i, _i, _vp, _f, _f, _i, _vp, _vp, _sz, _vp]),
     "b2d_stream_step_workspace_bytes": (_sz, [_vp, _vp, _i]),
     "b2d_stream_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _u64, _vp, _i, _f, _i, _vp, _vp, _sz, _vp]),
+    "b2d_pcm16_to_float": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
+    "b2d_float_to_pcm16": (_i, [_vp, _sz, _vp, _vp]),
+    "b2d_resampler_create": (_i, [_i, _i, _i, _i, _vp, C.POINTER(_vp)]),
+    "b2d_resampler_destroy": (None, [_vp]),
+    "b2d_resample_length": (_i, [_vp, _i]),
+    "b2d_resample": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

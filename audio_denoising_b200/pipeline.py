@@ -272,6 +272,21 @@ class StreamingDenoiser:
             return np.zeros((self.S, 0), dtype=np.float32)
         return np.concatenate(outs, axis=1)
 
+    def recv_pcm(self, pcm: np.ndarray) -> np.ndarray:
+        """``DenoisingAudioProcessor.recv`` on raw int16 frames (app3.py:167-250) for a single session: int16 [n] or
+        [n, channels] in -> int16 out.  While no hop has been produced yet the input is passed through (padded / cut to the
+        frame length), exactly as app3.py:228-241 does."""
+        if self.S != 1:
+            raise ValueError("recv_pcm mirrors one WebRTC session; use push() for batched sessions")
+        a = np.asarray(pcm)
+        if a.ndim > 1:
+            a = a[:, 0]  # app3.py:169-170
+        chunk = a.astype(np.float32) / np.iinfo(np.int16).max
+        out = self.push(chunk)
+        if out.shape[1] == 0:
+            return (np.clip(chunk, -1.0, 1.0) * np.iinfo(np.int16).max).astype(np.int16)
+        return self.to_int16(out[0])
+
     @staticmethod
     def to_int16(x: np.ndarray) -> np.ndarray:
         """app3.py:244-245."""

@@ -15,7 +15,7 @@ from torch import nn
 from . import _cabi
 from ._runtime import Workspace, draw_seed, get_plan, is_hann, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
 
-__all__ = ["Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram"]
+__all__ = ["Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram", "Resample", "pcm16_to_float", "float_to_pcm16"]
 
 
 def _geometry(n_fft, win_length, hop_length, window_fn, wkwargs, who):
@@ -214,3 +214,88 @@ class InverseSpectrogram(nn.Module):
         with torch.cuda.device(s.device):
             _cabi.check(_cabi.lib().b2d_istft(plan.handle, s.data_ptr(), ptr(mag), B, T, wave.data_ptr(), stream_ptr(s.device)))
         return wave.reshape(lead + wave.shape[-1:])
+
+
+def _sinc_hann_table(orig: int, new: int, lowpass_filter_width: int, rolloff: float):
+    """Polyphase table of TA:functional/functional.py:1340-1402 (sinc_interp_hann): float64 arithmetic, float32 result
+    [new, 2*width + orig]."""
+    import math
+
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, :] / orig
+    t = torch.arange(0, -new, -1)[:, None] / new + idx  # the phase term is rounded to float32 first, as torchaudio's is
+    t = (t * base).clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    kern = torch.where(t == 0, torch.ones_like(t), t.sin() / t) * window * (base / orig)
+    return kern.to(torch.float32).contiguous(), width
+
+
+class Resample(nn.Module):
+    """``torchaudio.transforms.Resample(orig_freq, new_freq)`` as used for ``utils.R1`` / ``utils.R2`` (utils.py:48-49):
+    sinc interpolation with a Hann window, ``lowpass_filter_width=6``, ``rolloff=0.99``.  [..., L] -> [..., ceil(new*L/orig)]."""
+
+    def __init__(self, orig_freq: int = 16000, new_freq: int = 16000, resampling_method: str = "sinc_interp_hann",
+                 lowpass_filter_width: int = 6, rolloff: float = 0.99, beta=None, *, dtype=None) -> None:
+        super().__init__()
+        if resampling_method not in ("sinc_interp_hann", "sinc_interpolation"):
+            raise NotImplementedError("Resample: only the sinc_interp_hann method is implemented")
+        if int(orig_freq) != orig_freq or int(new_freq) != new_freq:
+            raise Exception("Frequencies must be of integer type to ensure quality resampling computation.")
+        import math
+
+        self.orig_freq, self.new_freq = int(orig_freq), int(new_freq)
+        self.gcd = math.gcd(self.orig_freq, self.new_freq)
+        self.lowpass_filter_width, self.rolloff = lowpass_filter_width, rolloff
+        self._orig, self._new = self.orig_freq // self.gcd, self.new_freq // self.gcd
+        self._table, self._width = (None, 0) if self.orig_freq == self.new_freq else _sinc_hann_table(self._orig, self._new, lowpass_filter_width, rolloff)
+        self._native = {}
+
+    def _handle(self, device):
+        import ctypes as C
+        import weakref
+
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._native:
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                _cabi.check(_cabi.lib().b2d_resampler_create(self._orig, self._new, self._table.shape[1], self._width, self._table.data_ptr(), C.byref(h)))
+            weakref.finalize(self, _cabi.lib().b2d_resampler_destroy, h)
+            self._native[idx] = h
+        return self._native[idx]
+
+    def forward(self, waveform: torch.Tensor) -> torch.Tensor:
+        x = require_cuda_f32(waveform, "waveform")
+        if self.orig_freq == self.new_freq:
+            return x
+        x, lead = _pack(x, 1)
+        B, L = x.shape
+        lib = _cabi.lib()
+        h = self._handle(x.device)
+        out = torch.empty((B, lib.b2d_resample_length(h, L)), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.b2d_resample(h, x.data_ptr(), B, L, out.data_ptr(), stream_ptr(x.device)))
+        return out.reshape(lead + out.shape[-1:])
+
+
+def pcm16_to_float(pcm: torch.Tensor, channel: int = 0) -> torch.Tensor:
+    """int16 CUDA tensor [n, channels] (or [n]) -> float32 [n]: ``pcm[:, channel] / 32767`` (app3.py:168-172); ``channel=-1``
+    averages the channels (app.py:184-186)."""
+    if not pcm.is_cuda or pcm.dtype != torch.int16:
+        raise TypeError("pcm16_to_float expects an int16 CUDA tensor")
+    p = pcm.contiguous()
+    n, ch = (p.shape[0], 1) if p.dim() == 1 else (p.shape[0], p.shape[1])
+    out = torch.empty(n, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.lib().b2d_pcm16_to_float(p.data_ptr(), n, ch, channel if ch > 1 else 0, out.data_ptr(), stream_ptr(p.device)))
+    return out
+
+
+def float_to_pcm16(x: torch.Tensor) -> torch.Tensor:
+    """``(clip(x, -1, 1) * 32767).astype(int16)`` (app3.py:244-245) on the device."""
+    x = require_cuda_f32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().b2d_float_to_pcm16(x.data_ptr(), x.numel(), out.data_ptr(), stream_ptr(x.device)))
+    return out

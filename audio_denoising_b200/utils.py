@@ -33,6 +33,15 @@ STDS = torch.tensor(
 )
 
 
+def _resamplers():
+    from .transforms import Resample
+
+    return Resample(44100, SR), Resample(SR, 44100)
+
+
+R1, R2 = _resamplers()  # utils.py:48-49 (44.1 kHz <-> 48 kHz), running on the B200 polyphase kernel
+
+
 def normalize(x):
     """utils.py:429-432: divide [B, F, T] (or [B, C, F, T]) spectrogram features by the per-bin STDS."""
     shape = (1, -1, 1) if x.dim() == 3 else (1, 1, -1, 1)

@@ -172,6 +172,21 @@ int b2d_stream_step(const b2d_plan* plan, const b2d_model* model, const float* c
                     float* ola, const b2d_c64* init_angles, unsigned long long seed, const unsigned long long* d_seed,
                     int n_iter, float momentum, int conv_mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- audio ingest adjacent to the path ------------------------------
+ * b2d_pcm16_to_float: int16 PCM [n, channels] (sample-major, as `frame.to_ndarray(format="s16")` reshaped by app3.py:168-170)
+ *   -> float32 [n] = pcm[:, channel] / 32767 (app3.py:172), or the mean over channels when channel < 0 (app.py:184-186).
+ * b2d_float_to_pcm16: (clip(x, -1, 1) * 32767).astype(int16)  (app3.py:244-245).
+ * b2d_resample*: torchaudio.transforms.Resample(orig, new) of utils.py:48-49 (TA:functional/functional.py:1305-1432): the
+ *   caller passes the sinc-Hann polyphase table h_kernel [new_reduced, taps] (rates reduced by their gcd, taps = 2*width +
+ *   orig_reduced); in [B, L] -> out [B, ceil(new * L / orig)]. */
+typedef struct b2d_resampler b2d_resampler;
+int b2d_pcm16_to_float(const short* pcm, size_t n, int channels, int channel, float* out, void* stream);
+int b2d_float_to_pcm16(const float* in, size_t n, short* out, void* stream);
+int b2d_resampler_create(int orig_reduced, int new_reduced, int taps, int width, const float* h_kernel, b2d_resampler** out);
+void b2d_resampler_destroy(b2d_resampler* r);
+int b2d_resample_length(const b2d_resampler* r, int L);
+int b2d_resample(const b2d_resampler* r, const float* in, int B, int L, float* out, void* stream);
+
 /* Number of kernels this library has launched from the calling process (all threads); bench.py
  * reports the difference across the timed region as "gpu_launches". */
 unsigned long long b2d_launch_count(void);

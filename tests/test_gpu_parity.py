@@ -533,3 +533,90 @@ def test_streaming_cuda_graph_matches_eager_launches(dev):
     assert np.array_equal(outs[True][0], outs[False][0])
     assert torch.equal(outs[True][1], outs[False][1]) and torch.equal(outs[True][2], outs[False][2])
     assert np.abs(outs[True][0][:, 320:]).max() > 0  # something was emitted after the one-hop delay
+
+
+# ---------------------------------------------------------------------------------------------- ingest (section 8f rank 2)
+@pytest.mark.parametrize("tag", ["s16k", "s48k"])
+def test_recv_pcm_matches_reference_recv_including_passthrough(dev, golden, tag):
+    """Every recv call of app3.py:167-250, including the pass-through frames of app3.py:228-241 (bit-exact)."""
+    import audio_denoising_b200 as adb
+
+    s = golden("stream.npz")
+    n_fft, hop, sr, ncalls = [int(v) for v in s[f"{tag}_cfg"]]
+    m, *_ = _our_model("dari_tult2", dev)
+
+    def angles(i, shape):
+        torch.manual_seed(1000 + i + 1)
+        return torch.rand(shape, dtype=torch.complex64)
+
+    sd = adb.StreamingDenoiser(m, n_fft=n_fft, hop_length=hop, n_mels=64, sample_rate=sr, sessions=1, angles_fn=angles)
+    pcm, ref = s[f"{tag}_pcm"], s[f"{tag}_out"]
+    passthrough = 0
+    for i in range(ncalls):
+        chunk = pcm[i * hop : (i + 1) * hop]
+        got = sd.recv_pcm(chunk.reshape(-1, 1))
+        assert got.dtype == np.int16 and got.shape == (hop,)
+        if np.array_equal(ref[i], chunk):
+            passthrough += 1
+            assert np.array_equal(got, ref[i]), f"call {i}: pass-through frame differs"
+        else:
+            assert np.abs(got.astype(np.int64) - ref[i].astype(np.int64)).max() <= 3
+    assert passthrough >= 1
+
+
+@pytest.mark.parametrize("shape,channel", [((4801,), 0), ((4801, 2), 0), ((4801, 2), 1), ((4801, 2), -1), ((0, 1), 0)])
+def test_pcm16_to_float_bit_exact(dev, shape, channel):
+    import audio_denoising_b200 as adb
+
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32768, size=shape, dtype=np.int16)
+    got = adb.pcm16_to_float(torch.from_numpy(pcm).to(dev), channel).cpu().numpy()
+    a = pcm.reshape(shape[0], -1).astype(np.float32) / np.float32(32767)
+    want = a.mean(axis=1, dtype=np.float32) if (channel < 0 and a.shape[1] > 1) else a[:, max(channel, 0) if a.shape[1] > 1 else 0]
+    if channel < 0 and a.shape[1] > 1:
+        assert np.abs(got - want).max() <= 1e-7
+    else:
+        assert np.array_equal(got, want)
+
+
+def test_float_to_pcm16_bit_exact(dev):
+    import audio_denoising_b200 as adb
+
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-1.5, 1.5, 100000).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, -1.0, 0.99999, -0.99999, 1e-9, 3.0, -3.0, 0.5 / 32767, -0.5 / 32767], np.float32)])
+    want = (np.clip(x, -1.0, 1.0) * 32767).astype(np.int16)
+    got = adb.float_to_pcm16(torch.from_numpy(x).to(dev)).cpu().numpy()
+    assert np.array_equal(got, want)
+    # and the round trip int16 -> float -> int16 is the identity on [-32767, 32767]
+    p = torch.arange(-32767, 32768, dtype=torch.int16, device=dev)
+    assert torch.equal(adb.float_to_pcm16(adb.pcm16_to_float(p)), p)
+
+
+@pytest.mark.parametrize("orig,new,L", [(44100, 48000, 44100), (48000, 44100, 48000), (16000, 48000, 5000), (48000, 16000, 12001),
+                                        (44100, 48000, 1), (44100, 48000, 146), (8000, 8000, 100)])
+def test_resample_matches_torchaudio(dev, orig, new, L):
+    """utils.R1 / R2 (utils.py:48-49): same polyphase table (bit-identical, checked on CPU) and the same FIR sums."""
+    import torchaudio
+    import audio_denoising_b200 as adb
+
+    g = torch.Generator().manual_seed(orig + new + L)
+    x = torch.randn(3, L, generator=g) * 0.3
+    want = torchaudio.transforms.Resample(orig, new)(x)
+    got = adb.Resample(orig, new)(x.to(dev)).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+    got1 = adb.Resample(orig, new)(x[0].to(dev)).cpu()  # 1-D input keeps its rank
+    assert got1.shape == want[0].shape and torch.equal(got1, got[0])
+
+
+def test_resample_round_trip_44k1_48k(dev):
+    """R2(R1(x)) ~ x for band-limited audio (the way dataset clips travel through utils.R1/R2)."""
+    from audio_denoising_b200 import utils
+
+    t = torch.arange(44100, dtype=torch.float64) / 44100
+    x = (0.4 * torch.sin(2 * np.pi * 440 * t) + 0.2 * torch.sin(2 * np.pi * 3000 * t + 1.0)).float().to(dev)
+    y = utils.R2(utils.R1(x))
+    assert y.shape[-1] == 44100
+    mid = slice(400, 43700)  # away from the zero-padded edges
+    assert (y[mid] - x[mid]).abs().max() < 2e-3

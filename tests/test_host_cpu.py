@@ -195,3 +195,27 @@ def test_checkpoint_helpers_round_trip(tmp_path):
     model2, _ = adb.load_denoising_model(bare, fallback_config=cfg, device="cpu")
     assert model2 is not None
     assert issubclass(adb.GRUUNet, adb.GRUUNet2)
+
+
+@pytest.mark.parametrize("orig,new", [(44100, 48000), (48000, 44100), (16000, 48000), (48000, 16000), (22050, 16000)])
+def test_resample_table_bit_identical_to_torchaudio(orig, new):
+    """Host-built sinc-Hann polyphase table == torchaudio's (TA:functional/functional.py:1340-1402)."""
+    import math
+    import torchaudio
+    from audio_denoising_b200.transforms import _sinc_hann_table
+
+    g = math.gcd(orig, new)
+    table, width = _sinc_hann_table(orig // g, new // g, 6, 0.99)
+    ref, ref_width = torchaudio.functional.functional._get_sinc_resample_kernel(orig, new, g)
+    assert width == ref_width and torch.equal(table, ref[:, 0, :])
+
+
+def test_resample_and_ingest_refuse_cpu_tensors():
+    import audio_denoising_b200 as adb
+
+    with pytest.raises((TypeError, ValueError, RuntimeError)):
+        adb.Resample(44100, 48000)(torch.zeros(100))
+    with pytest.raises(TypeError):
+        adb.pcm16_to_float(torch.zeros(10, dtype=torch.int16))
+    with pytest.raises(NotImplementedError):
+        adb.Resample(44100, 48000, resampling_method="sinc_interp_kaiser")
