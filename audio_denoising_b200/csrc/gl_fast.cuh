@@ -255,5 +255,82 @@ B2D_HD void special2_update(float2& U, float2& V, float2 p0a, float2 p0b, float 
   V = make_float2(maN * (aN * inv_norm(aN * aN)), mbN * (bN * inv_norm(bN * bN)));
 }
 
+// ---- n_fft = 2048: the 1024-point complex transform is one radix-2 step over two 512-point register transforms -------
+// z[n] = x[2n] + i x[2n+1] (n < 1024);  E = FFT512(z[2m]), O = FFT512(z[2m+1]);  Z[k] = E[k] + W1024^k O[k],
+// Z[k+512] = E[k] - W1024^k O[k].  A pair slot holds bins k and 512-k of E and of O in the same lane, i.e. the four
+// bins k, 512-k, 512+k, 1024-k of Z = the two real-FFT pairs (k, 1024-k) and (512-k, 512+k): still lane-local.
+// tp / mg: staged rows (tprev holds 2 x rebuilt, bin 0 packed) ; st: the frame's tprev row in HBM or nullptr.
+B2D_HD void store_prev2(float2* st, int k, float2 v) {
+#ifdef __CUDA_ARCH__
+  __stcs(st + k, v);
+#else
+  st[k] = v;
+#endif
+}
+// inverse radix-2 step: E'[k] = Z[k] + Z[k+512], O'[k] = (Z[k] - Z[k+512]) conj W1024^k, and the same for bin 512-k
+B2D_HD void quad_uncombine(float2 Zk, float2 Zkp, float2 Zm, float2 Zmp, float2 c, float2& Ek, float2& Emk, float2& Ok, float2& Omk) {
+  Ek = make_float2(Zk.x + Zkp.x, Zk.y + Zkp.y);
+  Ok = cmulc(make_float2(Zk.x - Zkp.x, Zk.y - Zkp.y), c);
+  Emk = make_float2(Zm.x + Zmp.x, Zm.y + Zmp.y);
+  Omk = cmul(make_float2(Zmp.x - Zm.x, Zmp.y - Zm.y), c);  // (Zm - Zmp) * conj(-conj c)
+}
+B2D_HD void quad_update(float2& Ek, float2& Emk, float2& Ok, float2& Omk, int k, float2 c, float2 rtk, float2 rtm,
+                        const float2* tp, const float* mg, float mom, bool use_prev, float2* st) {
+  const float2 zero = make_float2(0.f, 0.f);
+  const float2 t = cmul(c, Ok);
+  const float2 tm = cmul(make_float2(-c.x, c.y), Omk);  // W1024^(512-k) = -conj W1024^k
+  float2 Zk = make_float2(Ek.x + t.x, Ek.y + t.y), Zkp = make_float2(Ek.x - t.x, Ek.y - t.y);          // bins k, k+512
+  float2 Zm = make_float2(Emk.x + tm.x, Emk.y + tm.y), Zmp = make_float2(Emk.x - tm.x, Emk.y - tm.y);  // bins 512-k, 1024-k
+  float2 x1, x2, x3, x4;
+  pair_update(Zk, Zmp, rtk, use_prev ? tp[k] : zero, use_prev ? tp[1024 - k] : zero, mg[k], mg[1024 - k], mom, use_prev, x1, x2);
+  pair_update(Zm, Zkp, rtm, use_prev ? tp[512 - k] : zero, use_prev ? tp[512 + k] : zero, mg[512 - k], mg[512 + k], mom, use_prev, x3, x4);
+  if (st) { store_prev2(st, k, x1); store_prev2(st, 1024 - k, x2); store_prev2(st, 512 - k, x3); store_prev2(st, 512 + k, x4); }
+  quad_uncombine(Zk, Zkp, Zm, Zmp, c, Ek, Emk, Ok, Omk);
+}
+// x_0 = istft(mag * angles_0): the same slot filled straight from the magnitudes (angle draws as in the generic kernel:
+// element index = frame_base + bin, frame_base = (b T + t) * 1025; seed 0 = all-ones angles)
+B2D_HD float2 init_bin(const float* mg, int k, unsigned long long seed, unsigned long long frame_base) {
+  const float m = mg[k];
+  if (!seed) return make_float2(m, 0.f);
+  const float2 a = rand_angle(seed, frame_base + k);
+  return make_float2(m * a.x, m * a.y);
+}
+B2D_HD void quad_init(float2& Ek, float2& Emk, float2& Ok, float2& Omk, int k, float2 c, float2 rtk, float2 rtm, const float* mg,
+                      unsigned long long seed, unsigned long long frame_base) {
+  float2 Zk, Zkp, Zm, Zmp;
+  irfft_merge(init_bin(mg, k, seed, frame_base), init_bin(mg, 1024 - k, seed, frame_base), rtk, Zk, Zmp);
+  irfft_merge(init_bin(mg, 512 - k, seed, frame_base), init_bin(mg, 512 + k, seed, frame_base), rtm, Zm, Zkp);
+  quad_uncombine(Zk, Zkp, Zm, Zmp, c, Ek, Emk, Ok, Omk);
+}
+B2D_HD void quad_special_init(float2& E0, float2& E256, float2& O0, float2& O256, float2 rt256, const float* mg, unsigned long long seed,
+                              unsigned long long frame_base) {
+  const float y0 = init_bin(mg, 0, seed, frame_base).x, yM = init_bin(mg, 1024, seed, frame_base).x;
+  const float2 y512 = init_bin(mg, 512, seed, frame_base);
+  const float2 Z0 = make_float2(y0 + yM, y0 - yM), Z512 = make_float2(2.0f * y512.x, -2.0f * y512.y);
+  float2 Z256, Z768;
+  irfft_merge(init_bin(mg, 256, seed, frame_base), init_bin(mg, 768, seed, frame_base), rt256, Z256, Z768);
+  E0 = make_float2(Z0.x + Z512.x, Z0.y + Z512.y);
+  O0 = make_float2(Z0.x - Z512.x, Z0.y - Z512.y);
+  E256 = make_float2(Z256.x + Z768.x, Z256.y + Z768.y);
+  const float2 d = make_float2(Z256.x - Z768.x, Z256.y - Z768.y);
+  O256 = make_float2(-d.y, d.x);
+}
+// lane 0, slot 0: E0 = E[0], E256 = E[256], O0 = O[0], O256 = O[256] -> bins 0 / 1024 (packed), 512 (self-paired), 256 & 768.
+B2D_HD void quad_special(float2& E0, float2& E256, float2& O0, float2& O256, float2 rt256, const float2* tp, const float* mg, float mom,
+                         bool use_prev, float2* st) {
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 Z0 = make_float2(E0.x + O0.x, E0.y + O0.y), Z512 = make_float2(E0.x - O0.x, E0.y - O0.y);
+  float2 Z256 = make_float2(E256.x + O256.y, E256.y - O256.x), Z768 = make_float2(E256.x - O256.y, E256.y + O256.x);  // W1024^256 = -i
+  float2 x0M, x512, x256, x768;
+  special_update(Z0, Z512, use_prev ? tp[0] : zero, use_prev ? tp[512] : zero, mg[0], mg[1024], mg[512], mom, use_prev, x0M, x512);
+  pair_update(Z256, Z768, rt256, use_prev ? tp[256] : zero, use_prev ? tp[768] : zero, mg[256], mg[768], mom, use_prev, x256, x768);
+  if (st) { store_prev2(st, 0, x0M); store_prev2(st, 512, x512); store_prev2(st, 256, x256); store_prev2(st, 768, x768); }
+  E0 = make_float2(Z0.x + Z512.x, Z0.y + Z512.y);
+  O0 = make_float2(Z0.x - Z512.x, Z0.y - Z512.y);
+  E256 = make_float2(Z256.x + Z768.x, Z256.y + Z768.y);
+  const float2 d = make_float2(Z256.x - Z768.x, Z256.y - Z768.y);
+  O256 = make_float2(-d.y, d.x);  // * conj(-i) = * i
+}
+
 }  // namespace fast512
 }  // namespace b2d

@@ -243,6 +243,12 @@ int gl_fast_warps_per_sm();
 bool gl_fast_persistent();
 int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
                         int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast_n512.cu
+int launch_gl_fast_n2048(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
+                         int R, float mom, int use_prev, int store_prev, float* wave, const float* out_scale,
+                         cudaStream_t st);  // gl_fast_n2048.cu
+int gl_fast_n2048_warps();
+int launch_gl_fast_n2048_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
+                              const unsigned long long* seed_ptr, cudaStream_t st);
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            const unsigned long long* seed_ptr, cudaStream_t st);
 
@@ -253,14 +259,15 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   if (getenv("B2D_GL_GENERIC") == nullptr) {
     if (p->n_fft == 1024 && p->hop == 512) q.fast = 1;
     if (p->n_fft == 512 && p->hop == 256) q.fast = 2;
+    if (p->n_fft == 2048 && p->hop == 1024) q.fast = 3;
   }
   if (q.fast) {
     // one warp per run.  Pick the number of runs per clip R that minimises the busiest SM's load
     // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
-    const int wps = gl_fast_warps_per_sm();
+    const int wps = q.fast == 3 ? gl_fast_n2048_warps() : gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
     const int maxR = (T + 3) / 4;  // at least 4 frames per run
-    if (gl_fast_persistent() || q.fast == 2) {
+    if (gl_fast_persistent() || q.fast >= 2) {
       // Measured: a warp needs ~4.5 us per frame whether 1 or 12 warps share the SM (the kernel is latency-bound per
       // warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).  Minimise that; ties -> longer runs
       // (less boundary traffic).
@@ -352,6 +359,9 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   if (q.fast == 1 && init_angles == nullptr) {
     int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
     if (rc != B2D_OK) return rc;
+  } else if (q.fast == 3 && init_angles == nullptr) {
+    int rc = launch_gl_fast_n2048_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
+    if (rc != B2D_OK) return rc;
   } else {
     gl_generic_kernel<<<grid, 256, smem, st>>>(a);
     B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
@@ -370,6 +380,12 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     } else if (q.fast == 2) {
       int rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
       if (rc != B2D_OK) return rc;
+    } else if (q.fast == 3) {
+      const bool last = (it + 1 == n_iter) && getenv("B2D_GL_NO_DIRECT") == nullptr;
+      int rc = launch_gl_fast_n2048(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev,
+                                    last ? wave : nullptr, out_scale, st);
+      if (rc != B2D_OK) return rc;
+      direct_interior = last;
     } else {
       gl_generic_kernel<<<grid, 256, smem, st>>>(a);
       B2D_LAUNCH_CHECK("gl_generic_kernel");

@@ -60,9 +60,9 @@ using namespace b2d;
 extern "C" {
 
 int b2d_pcm16_to_float(const short* pcm, size_t n, int channels, int channel, float* out, void* stream) {
-  B2D_REQUIRE(pcm && out, B2D_ERR_BAD_ARG, "NULL pointer");
   B2D_REQUIRE(channels >= 1 && channel < channels, B2D_ERR_BAD_ARG, "bad channel selection %d of %d", channel, channels);
   if (n == 0) return B2D_OK;
+  B2D_REQUIRE(pcm && out, B2D_ERR_BAD_ARG, "NULL pointer");
   const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   pcm16_to_float_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pcm, n, channels, channel, out);
   B2D_LAUNCH_CHECK("pcm16_to_float_kernel");
@@ -70,8 +70,8 @@ int b2d_pcm16_to_float(const short* pcm, size_t n, int channels, int channel, fl
 }
 
 int b2d_float_to_pcm16(const float* in, size_t n, short* out, void* stream) {
-  B2D_REQUIRE(in && out, B2D_ERR_BAD_ARG, "NULL pointer");
   if (n == 0) return B2D_OK;
+  B2D_REQUIRE(in && out, B2D_ERR_BAD_ARG, "NULL pointer");
   const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   float_to_pcm16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, n, out);
   B2D_LAUNCH_CHECK("float_to_pcm16_kernel");

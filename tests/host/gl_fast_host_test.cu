@@ -189,6 +189,76 @@ int main() {
     }
     printf("n_fft512 frame-pair iteration rel err %.3e\n", sqrt(e2 / n2)); if (sqrt(e2 / n2) > 5e-6) bad++;
   }
+  // ---- n_fft = 2048: radix-2 step over two 512-point register transforms ------------------------------------------------
+  {
+    const int N4 = 2048, M4 = 1024;
+    std::vector<float> f(N4);
+    for (auto& q : f) q = frand(seed);
+    std::vector<float2> P4(M4), rt4(M4);
+    std::vector<float> mg4(M4 + 4);
+    for (int k = 0; k < M4; ++k) {
+      P4[k] = make_float2(30 * frand(seed), 30 * frand(seed));
+      rt4[k] = make_float2((float)cos(-2 * M_PI * k / N4), (float)sin(-2 * M_PI * k / N4));
+    }
+    for (int k = 0; k <= M4; ++k) mg4[k] = 3.0f * (frand(seed) + 0.6f);
+    std::vector<cd> X(M4 + 1), Y(M4 + 1);
+    for (int k = 0; k <= M4; ++k) { cd a = 0; for (int n = 0; n < N4; ++n) a += (double)f[n] * std::polar(1.0, -2 * M_PI * (double)((long)n * k % N4) / N4); X[k] = a; }
+    for (int k = 0; k <= M4; ++k) {
+      cd p = (k == 0) ? cd(P4[0].x, 0) : (k == M4) ? cd(P4[0].y, 0) : cd(P4[k].x, P4[k].y);
+      cd a = 2.0 * X[k] - (double)mom * p;
+      if (k == 0 || k == M4) a = cd(a.real(), 0);
+      Y[k] = (double)mg4[k] * a / (std::abs(a) + 1e-16);
+    }
+    std::vector<double> yr(N4);
+    for (int n = 0; n < N4; ++n) {
+      cd a = Y[0].real() + Y[M4].real() * ((n & 1) ? -1.0 : 1.0);
+      for (int k = 1; k < M4; ++k) a += 2.0 * (Y[k] * std::polar(1.0, 2 * M_PI * (double)((long)n * k % N4) / N4)).real();
+      yr[n] = a.real();
+    }
+    static float2 ve[32][16], vo[32][16];
+    std::vector<float2> S2(XCH);
+    for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) {
+      const int m = l + 32 * q;
+      ve[l][q] = make_float2(f[4 * m], f[4 * m + 1]);
+      vo[l][q] = make_float2(f[4 * m + 2], f[4 * m + 3]);
+    }
+    auto fwd = [&](float2 (*w)[16]) {
+      for (int l = 0; l < 32; ++l) fwd1_store(l, w[l], lt[l], S2.data());
+      for (int l = 0; l < 32; ++l) fwd2_load(l, w[l], S2.data());
+      for (int l = 0; l < 32; ++l) fwd2_store(l, w[l], lt[l], S2.data());
+      for (int l = 0; l < 32; ++l) fwd3_load(l, w[l], S2.data());
+    };
+    auto inv = [&](float2 (*w)[16]) {
+      for (int l = 0; l < 32; ++l) inv1_store(l, w[l], S2.data());
+      for (int l = 0; l < 32; ++l) inv2_load(l, w[l], lt[l], S2.data());
+      for (int l = 0; l < 32; ++l) inv2_store(l, w[l], S2.data());
+      for (int l = 0; l < 32; ++l) inv3_load(l, w[l], lt[l], S2.data());
+    };
+    fwd(ve); fwd(vo);
+    std::vector<float2> nP(M4, make_float2(1e30f, 1e30f));
+    for (int l = 0; l < 32; ++l) {
+      if (l == 0) { lane0_permute(ve[l]); lane0_permute(vo[l]); }
+      for (int r = 0; r < 8; ++r) {
+        const int k = slot_k(l, r);
+        if (l == 0 && r == 0) quad_special(ve[l][0], ve[l][15], vo[l][0], vo[l][15], rt4[256], P4.data(), mg4.data(), mom, true, nP.data());
+        else quad_update(ve[l][2 * r], ve[l][2 * (7 - r) + 1], vo[l][2 * r], vo[l][2 * (7 - r) + 1], k, rt4[2 * k], rt4[k], rt4[512 - k],
+                         P4.data(), mg4.data(), mom, true, nP.data());
+      }
+      if (l == 0) { lane0_unpermute(ve[l]); lane0_unpermute(vo[l]); }
+    }
+    double e4 = 0, n4 = 0;
+    for (int k = 1; k < M4; ++k) { e4 += std::norm(cd(nP[k].x, nP[k].y) - 2.0 * X[k]); n4 += std::norm(2.0 * X[k]); }
+    e4 += std::norm(cd(nP[0].x, 0) - 2.0 * X[0]) + std::norm(cd(nP[0].y, 0) - 2.0 * X[M4]);
+    printf("n_fft2048 rebuilt rel err %.3e\n", sqrt(e4 / n4)); if (!(sqrt(e4 / n4) < 2e-6)) bad++;
+    inv(ve); inv(vo);
+    e4 = 0; n4 = 0;
+    for (int l = 0; l < 32; ++l) for (int q = 0; q < 16; ++q) {
+      const int m = l + 32 * q;
+      e4 += pow(ve[l][q].x - yr[4 * m], 2) + pow(ve[l][q].y - yr[4 * m + 1], 2) + pow(vo[l][q].x - yr[4 * m + 2], 2) + pow(vo[l][q].y - yr[4 * m + 3], 2);
+      n4 += pow(yr[4 * m], 2) + pow(yr[4 * m + 1], 2) + pow(yr[4 * m + 2], 2) + pow(yr[4 * m + 3], 2);
+    }
+    printf("n_fft2048 frame iteration rel err %.3e\n", sqrt(e4 / n4)); if (!(sqrt(e4 / n4) < 5e-6)) bad++;
+  }
   printf(bad ? "FAIL\n" : "OK\n");
   return bad;
 }

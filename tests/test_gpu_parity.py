@@ -357,7 +357,7 @@ def test_full_size_properties_config2(dev):
 
 
 # ---------------------------------------------------------------------------------------------- fast vs generic kernels
-@pytest.mark.parametrize("n_fft,hop", [(1024, 512), (512, 256)])
+@pytest.mark.parametrize("n_fft,hop", [(1024, 512), (512, 256), (2048, 1024)])
 def test_fast_kernels_match_generic_kernels(dev, monkeypatch, n_fft, hop):
     """n_fft 1024 and 512 have register/TMA fast kernels (gl_fast.cu, gl_fast_n512.cu); the generic shared-memory kernels
     are the cross-check.  Same C-ABI calls, same seed for the in-kernel rand_init draws."""
@@ -385,14 +385,25 @@ def test_fast_kernels_match_generic_kernels(dev, monkeypatch, n_fft, hop):
         _cabi.check(lib.b2d_griffinlim(plan.handle, mag.data_ptr(), None, seed, B, T, n_iter, 0.99, None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
         return wave.cpu()
 
-    fast = dict(logmel=logmel(), gl0=gl(77, 0), gl32=gl(77, 32), ones=gl(0, 8))
+    fast = dict(logmel=logmel(), gl0=gl(77, 0), gl4=gl(77, 4), gl32=gl(77, 32), ones=gl(0, 8))
     monkeypatch.setenv("B2D_GL_GENERIC", "1")
     monkeypatch.setenv("B2D_STFT_GENERIC", "1")
-    slow = dict(logmel=logmel(), gl0=gl(77, 0), gl32=gl(77, 32), ones=gl(0, 8))
+    slow = dict(logmel=logmel(), gl0=gl(77, 0), gl4=gl(77, 4), gl32=gl(77, 32), ones=gl(0, 8))
     assert metrics.rel_l2(fast["logmel"], slow["logmel"]) < 2e-6
     assert metrics.rel_l2(fast["logmel"], dsp.log_mel(x, n_fft, hop, dsp.mel_fbanks(n_fft // 2 + 1, 64, 16000)).transpose(1, 2)) < 5e-6
     assert metrics.si_sdr(fast["gl0"], slow["gl0"]).min() > 110.0  # same random initial phase from the same seed
-    assert metrics.si_sdr(fast["gl32"], slow["gl32"]).min() > 60.0
+    sdr4 = metrics.si_sdr(fast["gl4"], slow["gl4"])
+    assert sdr4.median() > 100.0 and sdr4.min() > 80.0, sdr4.tolist()
+    # 32 iterations from a random phase amplify last-bit differences where the spectrum is nearly empty (measured: one
+    # clip of the n_fft = 2048 case drops to 38 dB in its first three hop-blocks while agreeing to > 105 dB after 4
+    # iterations): bound the typical clip tightly, the worst clip loosely, and require the same spectral convergence
+    sdr32 = metrics.si_sdr(fast["gl32"], slow["gl32"])
+    assert sdr32.median() > 60.0 and sdr32.min() > (60.0 if n_fft != 2048 else 30.0), sdr32.tolist()
+    mag_ref = dsp.stft(x, n_fft, hop).abs()
+    for i in range(B):
+        sc_f = metrics.rel_l2(dsp.stft(fast["gl32"][i : i + 1], n_fft, hop).abs(), mag_ref[i : i + 1])
+        sc_s = metrics.rel_l2(dsp.stft(slow["gl32"][i : i + 1], n_fft, hop).abs(), mag_ref[i : i + 1])
+        assert abs(sc_f - sc_s) <= 0.02 * sc_s + 1e-6, (i, sc_f, sc_s)
     assert metrics.si_sdr(fast["ones"], slow["ones"]).min() > 90.0
     assert metrics.si_sdr(fast["ones"], dsp.griffinlim(dsp.stft(x, n_fft, hop).abs(), n_fft, hop, 8, 0.99, None, rand_init=False)).min() > 80.0
     # a different seed gives a different (but equally consistent) reconstruction

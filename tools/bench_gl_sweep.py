@@ -8,7 +8,7 @@ from audio_denoising_b200 import _cabi, _runtime
 dev = torch.device("cuda:0")
 lib = _cabi.lib()
 L = 64000
-for n_fft in (512, 1024, 2048):
+for n_fft in [int(v) for v in os.environ.get('SWEEP_NFFT', '512,1024,2048').split(',')]:
     plan = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev)
     T = plan.num_frames(L); F = n_fft // 2 + 1; Lout = plan.out_length(T)
     for B in (1, 16, 256, 4096):
