@@ -126,12 +126,31 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
   }
   if (mw.empty()) mw.push_back(0.f);
   p->mel_nnz = (int)mw.size();
+  // segments of <= 8 consecutive bins: lane s of a warp accumulates segment s, then each mel column sums its segments in order
+  std::vector<int> seg_lo, seg_first(n_mels + 1, 0);
+  std::vector<float> seg_taps;  // [nseg][8]
+  for (int m = 0; m < n_mels; ++m) {
+    seg_first[m] = (int)seg_lo.size();
+    for (int q0 = 0; q0 < cnt[m]; q0 += 8) {
+      seg_lo.push_back(lo[m] + q0);
+      for (int q = 0; q < 8; ++q) seg_taps.push_back(q0 + q < cnt[m] ? mw[off[m] + q0 + q] : 0.f);
+    }
+  }
+  seg_first[n_mels] = (int)seg_lo.size();
+  const int nseg = (int)seg_lo.size();
+  p->mel_seg_pad = (nseg + 31) / 32 * 32;
+  if (p->mel_seg_pad == 0) p->mel_seg_pad = 32;
+  seg_lo.resize(p->mel_seg_pad, 0);
+  std::vector<float> seg_w((size_t)2 * p->mel_seg_pad * 4, 0.f);
+  for (int sg = 0; sg < nseg; ++sg)
+    for (int q = 0; q < 8; ++q) seg_w[((size_t)(q / 4) * p->mel_seg_pad + sg) * 4 + (q & 3)] = seg_taps[(size_t)sg * 8 + q];
   std::vector<float> pinv((size_t)p->Fp * n_mels, 0.f);
   memcpy(pinv.data(), h_pinv, sizeof(float) * (size_t)F * n_mels);
   int rc;
   if ((rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw512, tw512)) || (rc = upload(&p->d_rtw, rtw)) || (rc = upload(&p->d_win, win)) ||
       (rc = upload(&p->d_winn, winn)) || (rc = upload(&p->d_inv_env, inv_env)) || (rc = upload(&p->d_mel_lo, lo)) ||
       (rc = upload(&p->d_mel_cnt, cnt)) || (rc = upload(&p->d_mel_off, off)) || (rc = upload(&p->d_mel_w, mw)) ||
+      (rc = upload(&p->d_seg_w, seg_w)) || (rc = upload(&p->d_seg_lo, seg_lo)) || (rc = upload(&p->d_seg_first, seg_first)) ||
       (rc = upload(&p->d_pinv, pinv))) {
     b2d_plan_destroy(p);
     return rc;
@@ -148,6 +167,7 @@ void b2d_plan_destroy(b2d_plan* p) {
   if (!p) return;
   cudaFree(p->d_tw); cudaFree(p->d_tw512); cudaFree(p->d_rtw); cudaFree(p->d_win); cudaFree(p->d_winn); cudaFree(p->d_inv_env);
   cudaFree(p->d_mel_lo); cudaFree(p->d_mel_cnt); cudaFree(p->d_mel_off); cudaFree(p->d_mel_w); cudaFree(p->d_pinv);
+  cudaFree(p->d_seg_w); cudaFree(p->d_seg_lo); cudaFree(p->d_seg_first);
   cudaFree(p->d_tw8);
   delete p;
 }

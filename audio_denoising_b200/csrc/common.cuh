@@ -68,6 +68,11 @@ struct b2d_plan {
   int* d_mel_off;     // [n_mels] offset into d_mel_w
   float* d_mel_w;     // compact column weights
   int mel_nnz;
+  // the same columns cut into segments of <= 8 bins for the warp-per-frame STFT kernel (balanced lanes):
+  float* d_seg_w;     // [2][mel_seg_pad][4] taps 0-3 / 4-7 of each segment, zero padded
+  int* d_seg_lo;      // [mel_seg_pad] first bin of the segment
+  int* d_seg_first;   // [n_mels + 1] first segment of each mel column
+  int mel_seg_pad;    // number of segments rounded up to a multiple of 32
   float* d_pinv;      // [Fp, n_mels] rows F..Fp-1 zero
   float2* d_tw8;      // TF32 big/small weight images of pinv for the tcgen05 inverse-mel GEMM (conv_tc.cu), may be null
 };

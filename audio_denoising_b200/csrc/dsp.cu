@@ -359,7 +359,7 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
 
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                 float* logmel_bm, float2* spec, cudaStream_t st) {
-  if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 &&
+  if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 && p->mel_seg_pad <= 320 && (long long)B * (1 + L / p->hop) < (1ll << 30) &&
       getenv("B2D_STFT_GENERIC") == nullptr)
     return launch_stft_fast512(p, wave, inv_scale, B, L, logmel_bt, st);
   StftArgs a;

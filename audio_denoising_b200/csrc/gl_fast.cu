@@ -398,13 +398,18 @@ struct StftFastArgs {
   const float2* tw512;
   const float2* rtw;
   const float* win;
-  const int* mel_lo;
-  const int* mel_cnt;
-  const int* mel_off;
-  const float* mel_w;
-  int mel_nnz;
+  const float* seg_w;     // [2][seg_pad][4] mel column segments of <= 8 bins (see b2d_plan)
+  const int* seg_lo;      // [seg_pad]
+  const int* seg_first;   // [n_mels + 1]
+  int seg_pad;
   float* logmel_bt;
 };
+
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // One warp per frame; the frame's 4 KB of samples arrive by TMA bulk copy into a two-slot per-warp ring one frame
 // ahead (interior frames are contiguous in the clip); the two reflect-padded frames at the clip edges are staged
@@ -417,13 +422,17 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* WIN = reinterpret_cast<float2*>(smem_raw);  // [512] plain window pairs
   float2* RT = WIN + 512;
-  float* melw = reinterpret_cast<float*>(RT + 512);   // [mel_nnz rounded up to 4]
-  unsigned char* warp_base = reinterpret_cast<unsigned char*>(melw + ((a.mel_nnz + 3) & ~3));
+  float4* SEGW = reinterpret_cast<float4*>(RT + 512);  // [2][seg_pad]
+  int* SEGLO = reinterpret_cast<int*>(SEGW + 2 * a.seg_pad);
+  int* SEGF = SEGLO + a.seg_pad;                      // [n_mels + 1], padded to a multiple of 4 ints
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(SEGF + ((a.n_mels + 4) & ~3));
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     WIN[i] = make_float2(a.win[2 * i], a.win[2 * i + 1]);
     RT[i] = a.rtw[i];
   }
-  for (int i = threadIdx.x; i < a.mel_nnz; i += blockDim.x) melw[i] = a.mel_w[i];
+  for (int i = threadIdx.x; i < 2 * a.seg_pad; i += blockDim.x) SEGW[i] = reinterpret_cast<const float4*>(a.seg_w)[i];
+  for (int i = threadIdx.x; i < a.seg_pad; i += blockDim.x) SEGLO[i] = a.seg_lo[i];
+  for (int i = threadIdx.x; i <= a.n_mels; i += blockDim.x) SEGF[i] = a.seg_first[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wsm = warp_base + (size_t)warp * STFT_WSMEM;
@@ -440,34 +449,36 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
   LaneTw tw;
   lane_twiddles(lane, a.tw512, tw);
   const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
-  const size_t nframes = (size_t)a.B * a.T;
-  const size_t stride = (size_t)gridDim.x * WARPS;
+  const unsigned nframes = (unsigned)a.B * (unsigned)a.T;  // < 2^31 (checked by the launcher): 32-bit index math throughout
+  const unsigned stride = gridDim.x * WARPS;
   const bool tma_ok = (a.L % 4) == 0;  // 16-byte aligned clip rows
-  // frame f is "interior" when its 1024 samples lie inside the clip: then it is one contiguous, aligned 4 KB read
-  auto interior = [&](size_t f, const float*& src) {
-    const int b = (int)(f / a.T), t = (int)(f - (size_t)b * a.T);
+  // frame (b, t) is "interior" when its 1024 samples lie inside the clip: then it is one contiguous, aligned 4 KB read
+  auto interior = [&](unsigned b, unsigned t, const float*& src) {
     const long s0 = (long)t * HOP - HOP;
     src = a.wave + (size_t)b * a.L + s0;
     return tma_ok && s0 >= 0 && s0 + N <= a.L;
   };
   uint32_t use0 = 0, use1 = 0;
-  size_t f = (size_t)blockIdx.x * WARPS + warp;
+  unsigned f = blockIdx.x * WARPS + warp;
+  unsigned b = f / (unsigned)a.T, t = f - b * (unsigned)a.T;
   int slot = 0;
   if (f < nframes && lane == 0) {
     const float* src;
-    if (interior(f, src)) { mbar_expect_tx(fbar, N * 4); bulk_g2s(fbuf, src, N * 4, fbar); }
+    if (interior(b, t, src)) { mbar_expect_tx(fbar, N * 4); bulk_g2s(fbuf, src, N * 4, fbar); }
   }
+  unsigned bn = 0, tn = 0;
 #pragma unroll 1
-  for (; f < nframes; f += stride, slot ^= 1) {
-    const int b = (int)(f / a.T), t = (int)(f - (size_t)b * a.T);
+  for (; f < nframes; f += stride, slot ^= 1, b = bn, t = tn) {
     const float* x = a.wave + (size_t)b * a.L;
-    const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
+    const float rsc = a.inv_scale ? 1.0f / a.inv_scale[b] : 1.0f;  // x / peak as x * (1 / peak): within one ulp of the division
     float* cur = fbuf + slot * N;
     const float* src_cur;
-    const bool cur_tma = interior(f, src_cur);
+    const bool cur_tma = interior(b, t, src_cur);
+    bn = (f + stride) / (unsigned)a.T;
+    tn = (f + stride) - bn * (unsigned)a.T;
     if (lane == 0 && f + stride < nframes) {  // next frame of this warp into the other slot
       const float* src;
-      if (interior(f + stride, src)) { mbar_expect_tx(fbar + (slot ^ 1), N * 4); bulk_g2s(fbuf + (slot ^ 1) * N, src, N * 4, fbar + (slot ^ 1)); }
+      if (interior(bn, tn, src)) { mbar_expect_tx(fbar + (slot ^ 1), N * 4); bulk_g2s(fbuf + (slot ^ 1) * N, src, N * 4, fbar + (slot ^ 1)); }
     }
     if (cur_tma) {
       if (slot) { mbar_wait(fbar + 1, use1 & 1); ++use1; } else { mbar_wait(fbar, use0 & 1); ++use0; }
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
       for (int q = 0; q < 16; ++q) {
         const float2 xv = c2[lane + 32 * q];
         const float2 wv = WIN[lane + 32 * q];
-        v[q] = make_float2((xv.x / sc) * wv.x, (xv.y / sc) * wv.y);
+        v[q] = make_float2((xv.x * rsc) * wv.x, (xv.y * rsc) * wv.y);
       }
     }
     __syncwarp();
@@ -508,23 +519,33 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
       if (rr == 0 && lane == 0) {
         Sf[0] = fabsf(U.x + U.y);
         Sf[M] = fabsf(U.x - U.y);
-        Sf[256] = sqrtf(V.x * V.x + V.y * V.y);
+        Sf[256] = sqrt_fast(V.x * V.x + V.y * V.y);
       } else {
         float2 xk, xmk;
         rfft_split(U, V, RT[k], xk, xmk);
-        Sf[k] = sqrtf(xk.x * xk.x + xk.y * xk.y);
-        Sf[M - k] = sqrtf(xmk.x * xmk.x + xmk.y * xmk.y);
+        Sf[k] = sqrt_fast(xk.x * xk.x + xk.y * xk.y);
+        Sf[M - k] = sqrt_fast(xmk.x * xmk.x + xmk.y * xmk.y);
       }
     }
+    if (lane < 8) Sf[M + 1 + lane] = 0.f;  // the zero-weight taps of a column's last segment read up to 7 bins past the Nyquist bin
     __syncwarp();
-    // mel bins are paired narrow + wide (m, n_mels-1-m) so the lanes' loop lengths are balanced
-    for (int mi = lane; mi < a.n_mels; mi += 32) {
-      const int m = (mi < a.n_mels / 2) ? mi : (a.n_mels - 1) - (mi - a.n_mels / 2);
-      const int lo = a.mel_lo[m], cnt = a.mel_cnt[m];
-      const float* w = melw + a.mel_off[m];
+    // mel projection: lane s accumulates segment s (<= 8 consecutive bins of one mel column) ...
+    float* P = Sf + 576;
+    for (int s0 = 0; s0 < a.seg_pad; s0 += 32) {
+      const int sg = s0 + lane;
+      const float* mp = Sf + SEGLO[sg];
+      const float4 w0 = SEGW[sg], w1 = SEGW[a.seg_pad + sg];
+      float acc = mp[0] * w0.x;
+      acc = fmaf(mp[1], w0.y, acc); acc = fmaf(mp[2], w0.z, acc); acc = fmaf(mp[3], w0.w, acc);
+      acc = fmaf(mp[4], w1.x, acc); acc = fmaf(mp[5], w1.y, acc); acc = fmaf(mp[6], w1.z, acc); acc = fmaf(mp[7], w1.w, acc);
+      P[sg] = acc;
+    }
+    __syncwarp();
+    // ... then every mel column sums its segments in order
+    for (int m = lane; m < a.n_mels; m += 32) {
       float acc = 0.f;
-      for (int q = 0; q < cnt; ++q) acc = fmaf(Sf[lo + q], w[q], acc);
-      a.logmel_bt[f * a.n_mels + m] = log1pf(acc);
+      for (int sg = SEGF[m]; sg < SEGF[m + 1]; ++sg) acc += P[sg];
+      a.logmel_bt[(size_t)f * a.n_mels + m] = log1pf(acc);
     }
     __syncwarp();
   }
@@ -535,10 +556,11 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   StftFastArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.n_mels = p->n_mels;
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win;
-  a.mel_lo = p->d_mel_lo; a.mel_cnt = p->d_mel_cnt; a.mel_off = p->d_mel_off; a.mel_w = p->d_mel_w; a.mel_nnz = p->mel_nnz;
+  a.seg_w = p->d_seg_w; a.seg_lo = p->d_seg_lo; a.seg_first = p->d_seg_first; a.seg_pad = p->mel_seg_pad;
   a.logmel_bt = logmel_bt;
   constexpr int W = STFT_WARPS;
-  const size_t smem = sizeof(float2) * 1024 + sizeof(float) * ((p->mel_nnz + 3) & ~3) + (size_t)W * STFT_WSMEM;
+  B2D_REQUIRE(p->mel_seg_pad <= 320, B2D_ERR_UNSUPPORTED, "mel filterbank too dense for the n_fft = 1024 fast kernel");
+  const size_t smem = sizeof(float2) * 1024 + (size_t)p->mel_seg_pad * 36 + sizeof(int) * ((p->n_mels + 4) & ~3) + (size_t)W * STFT_WSMEM;
   B2D_CUDA(cudaFuncSetAttribute(stft_fast512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t nframes = (size_t)B * a.T;
   const size_t want = (nframes + W - 1) / W;

@@ -582,7 +582,7 @@ def test_pcm16_to_float_bit_exact(dev, shape, channel):
     rng = np.random.default_rng(5)
     pcm = rng.integers(-32768, 32768, size=shape, dtype=np.int16)
     got = adb.pcm16_to_float(torch.from_numpy(pcm).to(dev), channel).cpu().numpy()
-    a = pcm.reshape(shape[0], -1).astype(np.float32) / np.float32(32767)
+    a = pcm.reshape(shape[0], shape[1] if len(shape) > 1 else 1).astype(np.float32) / np.float32(32767)
     want = a.mean(axis=1, dtype=np.float32) if (channel < 0 and a.shape[1] > 1) else a[:, max(channel, 0) if a.shape[1] > 1 else 0]
     if channel < 0 and a.shape[1] > 1:
         assert np.abs(got - want).max() <= 1e-7
