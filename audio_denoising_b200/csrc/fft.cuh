@@ -18,8 +18,26 @@ B2D_HD float2 cmul(float2 a, float2 b) {
 B2D_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
+// Complex add / subtract / scale.  On the device these are Blackwell's packed fp32 instructions (add.f32x2 / fma.rn.f32x2:
+// one issue slot for both components, SASS FADD2 / FFMA2); a - b is fma(b, -1, a), which rounds exactly like the
+// subtraction, so host and device stay bit-identical.
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+B2D_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+B2D_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+B2D_HD float2 cscale2(float2 a, float2 s) { return __fmul2_rn(a, s); }
+B2D_HD float2 cfma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
 B2D_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 B2D_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+B2D_HD float2 cscale2(float2 a, float2 s) { return make_float2(a.x * s.x, a.y * s.y); }
+B2D_HD float2 cfma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+// rot90(a - b) computed directly into the rotated pair (two scalar subtractions; a packed subtraction would need its
+// components swapped afterwards)
+template <bool INV>
+B2D_HD float2 csub_rot90(float2 a, float2 b) {
+  return INV ? make_float2(b.y - a.y, a.x - b.x) : make_float2(a.y - b.y, b.x - a.x);
+}
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
 B2D_HD float2 rot90(float2 a) {
@@ -36,7 +54,7 @@ B2D_HD void dft2(float2& a, float2& b) {
 template <bool INV>
 B2D_HD void dft4(float2* v) {
   float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
-  float2 a2 = cadd(v[1], v[3]), a3 = rot90<INV>(csub(v[1], v[3]));
+  float2 a2 = cadd(v[1], v[3]), a3 = csub_rot90<INV>(v[1], v[3]);
   v[0] = cadd(a0, a2);
   v[2] = csub(a0, a2);
   v[1] = cadd(a1, a3);
@@ -48,18 +66,18 @@ B2D_HD void dft8(float2* v) {
   const float h = 0.70710678118654752440f;
   // three radix-2 stages, decimation in frequency, output written back in natural order
   float2 a[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    a[i] = cadd(v[i], v[i + 4]);
-    a[i + 4] = csub(v[i], v[i + 4]);
-  }
-  // twiddles W8^i on the lower half
+  a[0] = cadd(v[0], v[4]);
+  a[4] = csub(v[0], v[4]);
+  a[1] = cadd(v[1], v[5]);
+  a[2] = cadd(v[2], v[6]);
+  a[3] = cadd(v[3], v[7]);
+  // twiddles W8^i on the lower half, folded into the subtractions
   {
-    float2 t = a[5];
-    a[5] = INV ? make_float2((t.x - t.y) * h, (t.x + t.y) * h) : make_float2((t.x + t.y) * h, (t.y - t.x) * h);
-    a[6] = rot90<INV>(a[6]);
-    t = a[7];
-    a[7] = INV ? make_float2((-t.x - t.y) * h, (t.x - t.y) * h) : make_float2((t.y - t.x) * h, (-t.x - t.y) * h);
+    const float2 t = csub(v[1], v[5]);  // * W8^1: fwd ((x + y) h, (y - x) h), inv ((x - y) h, (x + y) h)
+    a[5] = cscale2(INV ? make_float2(t.x - t.y, t.x + t.y) : make_float2(t.x + t.y, t.y - t.x), make_float2(h, h));
+    a[6] = csub_rot90<INV>(v[2], v[6]);
+    const float2 u = csub(v[3], v[7]);  // * W8^3: fwd ((y - x) h, -(x + y) h), inv (-(x + y) h, (x - y) h)
+    a[7] = INV ? cscale2(make_float2(u.x + u.y, u.x - u.y), make_float2(-h, h)) : cscale2(make_float2(u.y - u.x, u.x + u.y), make_float2(h, -h));
   }
   float2 b[8];
 #pragma unroll
@@ -69,7 +87,7 @@ B2D_HD void dft8(float2* v) {
     q[0] = cadd(p[0], p[2]);
     q[2] = csub(p[0], p[2]);
     q[1] = cadd(p[1], p[3]);
-    q[3] = rot90<INV>(csub(p[1], p[3]));
+    q[3] = csub_rot90<INV>(p[1], p[3]);
   }
   // last stage; outputs X[k]: k = 4*k2 + 2*k1 + k0 from DIF order
   v[0] = cadd(b[0], b[1]);
@@ -209,8 +227,9 @@ B2D_HD void rfft_split(float2 zk, float2 zmk, float2 rt, float2& xk, float2& xmk
 // irfft scaling note): builds Z'[k], Z'[M-k] from Y[k], Y[M-k].  rt = W_N^k (forward twiddle).
 // Z'[k] = (Yk + conj(Ymk)) + i conj(W^k) (Yk - conj(Ymk)).
 B2D_HD void irfft_merge(float2 yk, float2 ymk, float2 rt, float2& zk, float2& zmk) {
-  const float ex = yk.x + ymk.x, ey = yk.y - ymk.y;   // Yk + conj(Ymk)
-  const float dx = yk.x - ymk.x, dy = yk.y + ymk.y;   // Yk - conj(Ymk)
+  const float2 e = cfma2(ymk, make_float2(1.0f, -1.0f), yk), d = cfma2(ymk, make_float2(-1.0f, 1.0f), yk);
+  const float ex = e.x, ey = e.y;   // Yk + conj(Ymk)
+  const float dx = d.x, dy = d.y;   // Yk - conj(Ymk)
   // t = conj(W^k) * D
   const float tx = fmaf(rt.x, dx, rt.y * dy), ty = fmaf(rt.x, dy, -rt.y * dx);
   // Z'[k] = E + i t = (ex - ty, ey + tx)

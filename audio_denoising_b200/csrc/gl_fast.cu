@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
         for (int q = 0; q < 8; ++q) {
           const float2 xv = src[lane + 32 * q];
           const float2 wv = wtab[lane + 32 * q];
-          v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+          v[8 * h + q] = cscale2(xv, wv);
         }
       } else {
         const float2* p1 = reinterpret_cast<const float2*>(xrun + (size_t)cs * HOP);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
           float2 xv = p1[lane + 32 * q];
           if (p2) { const float2 x2 = p2[lane + 32 * q]; xv.x += x2.x; xv.y += x2.y; }
           const float2 wv = wtab[lane + 32 * q];
-          v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+          v[8 * h + q] = cscale2(xv, wv);
         }
       }
     }
@@ -252,16 +252,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
       for (int q = 0; q < 8; ++q) {
         const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
         const float2 e = ie[lane + 32 * q];
-        wdst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x) * e.x * sc, fmaf(v[q].y, w0.y, carry[q].y) * e.y * sc);
-        carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+        wdst[lane + 32 * q] = cscale2(cfma2(v[q], w0, carry[q]), cscale2(e, make_float2(sc, sc)));
+        carry[q] = cscale2(v[8 + q], w1);
       }
     } else {
       float2* dst = reinterpret_cast<float2*>(xo + (size_t)c * HOP);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
-        dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
-        carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+        dst[lane + 32 * q] = cfma2(v[q], w0, carry[q]);
+        carry[q] = cscale2(v[8 + q], w1);
       }
     }
   }
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float2 w0 = WN[lane + 32 * q], w1 = WN[256 + lane + 32 * q];
-      dst[lane + 32 * q] = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
-      carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+      dst[lane + 32 * q] = cfma2(v[q], w0, carry[q]);
+      carry[q] = cscale2(v[8 + q], w1);
     }
   }
   float2* dst = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
       for (int q = 0; q < 16; ++q) {
         const float2 xv = c2[lane + 32 * q];
         const float2 wv = WIN[lane + 32 * q];
-        v[q] = make_float2((xv.x * rsc) * wv.x, (xv.y * rsc) * wv.y);
+        v[q] = cscale2(cscale2(xv, make_float2(rsc, rsc)), wv);
       }
     }
     __syncwarp();

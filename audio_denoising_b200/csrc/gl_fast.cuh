@@ -182,8 +182,8 @@ B2D_HD float2 unit_dir_fast(float2 a) {
 // rfft_split without the factor 1/2: returns 2 X[k], 2 X[M-k].  The fast path keeps 2 * rebuilt in tprev: the phase
 // update only uses the direction of (rebuilt - m * tprev), which is invariant to the common factor.
 B2D_HD void rfft_split2(float2 zk, float2 zmk, float2 rt, float2& xk, float2& xmk) {
-  const float ex = zk.x + zmk.x, ey = zk.y - zmk.y;
-  const float dx = zk.x - zmk.x, dy = zk.y + zmk.y;
+  const float2 e = cfma2(zmk, make_float2(1.0f, -1.0f), zk), d = cfma2(zmk, make_float2(-1.0f, 1.0f), zk);
+  const float ex = e.x, ey = e.y, dx = d.x, dy = d.y;
   const float tx = fmaf(rt.x, dx, -rt.y * dy), ty = fmaf(rt.x, dy, rt.y * dx);
   xk = make_float2(ex + ty, ey - tx);
   xmk = make_float2(ex - ty, -ey - tx);
@@ -196,8 +196,8 @@ B2D_HD void pair_update(float2& U, float2& V, float2 rt, float2 pk, float2 pmk, 
   rfft_split2(U, V, rt, xk, xmk);
   float2 ak = xk, amk = xmk;
   if (use_prev) {
-    ak = make_float2(fmaf(-mom, pk.x, xk.x), fmaf(-mom, pk.y, xk.y));
-    amk = make_float2(fmaf(-mom, pmk.x, xmk.x), fmaf(-mom, pmk.y, xmk.y));
+    ak = cfma2(pk, make_float2(-mom, -mom), xk);
+    amk = cfma2(pmk, make_float2(-mom, -mom), xmk);
   }
   const float2 uk = unit_dir_fast(ak), umk = unit_dir_fast(amk);
   irfft_merge(make_float2(mk * uk.x, mk * uk.y), make_float2(mmk * umk.x, mmk * umk.y), rt, U, V);

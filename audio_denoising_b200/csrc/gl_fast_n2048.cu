@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
           for (int q = 0; q < 8; ++q) {
             const float2 xv = *reinterpret_cast<const float2*>(src + 4 * (lane + 32 * q));
             const float2 wv = wtab[lane + 32 * q];
-            v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+            v[8 * h + q] = cscale2(xv, wv);
           }
         } else {
           const float* p1 = xrun + (size_t)cs * HOP2 + sub;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
             float2 xv = *reinterpret_cast<const float2*>(p1 + 4 * (lane + 32 * q));
             if (p2) { const float2 x2 = *reinterpret_cast<const float2*>(p2 + 4 * (lane + 32 * q)); xv.x += x2.x; xv.y += x2.y; }
             const float2 wv = wtab[lane + 32 * q];
-            v[8 * h + q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+            v[8 * h + q] = cscale2(xv, wv);
           }
         }
       }
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
           const int o = 4 * (lane + 32 * q);
           const float2 w0 = wn0[lane + 32 * q], w1 = wn1[lane + 32 * q];
           const float2 e = __ldg(reinterpret_cast<const float2*>(ie + o));
-          *reinterpret_cast<float2*>(wdst + o) = make_float2(fmaf(v[q].x, w0.x, carry[q].x) * e.x * sc, fmaf(v[q].y, w0.y, carry[q].y) * e.y * sc);
-          carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+          *reinterpret_cast<float2*>(wdst + o) = cscale2(cfma2(v[q], w0, carry[q]), cscale2(e, make_float2(sc, sc)));
+          carry[q] = cscale2(v[8 + q], w1);
         }
       } else {
         float* dst = xo + (size_t)c * HOP2 + sub;
@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
         for (int q = 0; q < 8; ++q) {
           const int o = 4 * (lane + 32 * q);
           const float2 w0 = wn0[lane + 32 * q], w1 = wn1[lane + 32 * q];
-          *reinterpret_cast<float2*>(dst + o) = make_float2(fmaf(v[q].x, w0.x, carry[q].x), fmaf(v[q].y, w0.y, carry[q].y));
-          carry[q] = make_float2(v[8 + q].x * w1.x, v[8 + q].y * w1.y);
+          *reinterpret_cast<float2*>(dst + o) = cfma2(v[q], w0, carry[q]);
+          carry[q] = cscale2(v[8 + q], w1);
         }
       }
     }
