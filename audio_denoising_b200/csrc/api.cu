@@ -203,6 +203,7 @@ void b2d_model_destroy(b2d_model* m) {
   if (!m) return;
   cudaFree(m->d_blob);
   cudaFree(m->d_tc);
+  cudaFree(m->d_mma);
   free(m->h_blob);
   delete m;
 }

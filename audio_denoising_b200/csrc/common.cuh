@@ -89,6 +89,7 @@ struct b2d_model {
   int rec_w, rec_pb;
   int dec_w[6], dec_pb[6];
   // bf16 operand images for the tcgen05 path (hi / lo split), see conv_tc.cu
+  float* d_mma;       // weight fragment images for the warp-level MMA decoder (unet_mma.cu)
   void* d_tc;
   size_t tc_bytes;
   int tc_off[32];

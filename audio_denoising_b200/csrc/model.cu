@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "model_layout.cuh"
 
 namespace b2d {
 
@@ -22,51 +23,6 @@ __device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("
 // warm L2 with [p, p + bytes): one 128-byte line per lane per round
 __device__ __forceinline__ void prefetch_l2_range(const float* p, int bytes, int lane) {
   for (int o = lane * 128; o < bytes; o += 32 * 128) prefetch_l2_line(reinterpret_cast<const char*>(p) + o);
-}
-
-// shipped configuration (all three checkpoints): hidden 17, 4 levels, 4 compressed bins
-constexpr int H = 17;
-constexpr int HP = 20;        // hidden padded to a multiple of 4 (float4 weight rows)
-constexpr int H3 = 51;
-constexpr int H3P = 52;
-constexpr int LEVELS = 4;
-constexpr int BINS = 4;
-constexpr int NMEL = BINS << LEVELS;  // 64
-
-// per-frame activation sizes
-constexpr int D0 = H * 32, D1 = H * 16, D2 = H * 8, GX = H3 * 4, HS = H * 4;
-
-// ---- packed parameter blob layout (floats) --------------------------------------------------------
-// encoder layer l : W[ci][k][coP]  ,  PB[j][coP]
-// recurrent       : W[ci][k][gate][c] (c padded to HP) , PB[gate][c][j]
-// decoder layer i : W[ci][k][coP]  ,  PB[o][coP]
-struct Packed {
-  int enc_w[LEVELS], enc_pb[LEVELS];
-  int rec_w, rec_pb;
-  int dec_w[LEVELS], dec_pb[LEVELS];
-  int total;
-};
-__host__ __device__ inline Packed packed_layout() {
-  Packed p{};
-  int o = 0;
-  const int cin[LEVELS] = {1, H, H, H};
-  const int cop[LEVELS] = {HP, HP, HP, H3P};
-  const int lout[LEVELS] = {32, 16, 8, 4};
-  for (int l = 0; l < LEVELS; ++l) {
-    p.enc_w[l] = o; o += cin[l] * 3 * cop[l];
-    p.enc_pb[l] = o; o += lout[l] * cop[l];
-  }
-  p.rec_w = o; o += H * 3 * 3 * HP;
-  p.rec_pb = o; o += 3 * H * 4;
-  const int dcin[LEVELS] = {H, 2 * H, 2 * H, 2 * H};
-  const int dcop[LEVELS] = {HP, HP, HP, 4};
-  const int dlout[LEVELS] = {8, 16, 32, 64};
-  for (int i = 0; i < LEVELS; ++i) {
-    p.dec_w[i] = o; o += dcin[i] * 3 * dcop[i];
-    p.dec_pb[i] = o; o += dlout[i] * dcop[i];
-  }
-  p.total = o;
-  return p;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,6 +579,11 @@ static void smear_table(const float* off, int G, int nbins, std::vector<double>&
 }
 
 int model_pack_tc_weights(b2d_model* m, const float* const* hp);  // conv_tc.cu
+int model_pack_mma(b2d_model* m);                                    // unet_mma.cu
+int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx, int terms,
+                     int num_sms, cudaStream_t st);
+int model_decode_mma(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
+                     size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int terms, int num_sms, cudaStream_t st);
 
 int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
   const Packed L = packed_layout();
@@ -709,6 +670,8 @@ int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
   if (m->h_blob) memcpy(m->h_blob, blob.data(), blob.size() * sizeof(float));
   B2D_CUDA(cudaMalloc(&m->d_blob, blob.size() * sizeof(float)));
   B2D_CUDA(cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  int rc = model_pack_mma(m);  // weight fragments for the warp-level MMA decoder (unet_mma.cu)
+  if (rc != B2D_OK) return rc;
   return model_pack_tc_weights(m, hp);  // TF32 big/small weight images for the tcgen05 path (conv_tc.cu)
 }
 
@@ -743,7 +706,8 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
                   float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "GRUUNet2 forward needs B >= 1 and T >= 1 (got %d, %d)", B, T);
   B2D_REQUIRE(ws != nullptr && ws_bytes >= model_workspace_bytes(m, B, T), B2D_ERR_WORKSPACE, "GRUUNet2 workspace too small");
-  B2D_REQUIRE(conv_mode >= 0 && conv_mode <= 2, B2D_ERR_BAD_ARG, "conv_mode must be 0, 1 or 2");
+  B2D_REQUIRE(conv_mode >= 0 && conv_mode <= 4, B2D_ERR_BAD_ARG, "conv_mode must be in [0, 4]");
+  const bool fma_encoder = (conv_mode == 0) || (conv_mode >= 3 && getenv("B2D_MMA_ENCODER_OFF") != nullptr);
   const size_t nf = (size_t)B * T;
   unsigned char* base = static_cast<unsigned char*>(ws);
   float* d0 = reinterpret_cast<float*>(base); base += align_up(nf * D0 * 4, 256);
@@ -754,7 +718,7 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   float* dec_scratch = reinterpret_cast<float*>(base);
   const Packed L = packed_layout();
   int dev_sms = 148;
-  if (conv_mode == 0) {
+  if (fma_encoder) {
     if (getenv("B2D_ENCODER_V2") == nullptr) {  // v1 measures 25 us faster: both are bound by shared-memory weight loads
       const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
       B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -770,13 +734,19 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
       encoder2_kernel<<<grid, ENC2_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
       B2D_LAUNCH_CHECK("encoder2_kernel");
     }
+  } else if (conv_mode >= 3) {
+    int rc = model_encode_mma(m, x, nf, d0, d1, d2, gx, conv_mode == 3 ? 3 : 1, dev_sms, st);
+    if (rc != B2D_OK) return rc;
   } else {
     int rc = model_forward_tc(m, x, nf, d0, d1, d2, gx, conv_mode, st);
     if (rc != B2D_OK) return rc;
   }
   recurrence_kernel<<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
   B2D_LAUNCH_CHECK("recurrence_kernel");
-  if (conv_mode == 0) {
+  if (conv_mode >= 3) {
+    int rc = model_decode_mma(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode == 3 ? 3 : 1, dev_sms, st);
+    if (rc != B2D_OK) return rc;
+  } else if (conv_mode == 0) {
     const int nw = L.total - L.dec_w[0];
     if (getenv("B2D_DECODER_V1")) {
       const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC_WARPS * DEC_ACT);

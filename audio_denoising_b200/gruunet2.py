@@ -25,8 +25,9 @@ from . import _cabi
 from ._runtime import Workspace, require_cuda_f32, stream_ptr
 
 # "fp32": CUDA-core FMA convolutions; "tf32x3": tcgen05 implicit GEMM, operands split into big+small TF32 parts (3 MMAs,
-# fp32-class accuracy); "tf32": tcgen05 single pass (11-bit mantissa operands, fp32 accumulate)
-CONV_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+# fp32-class accuracy); "tf32": tcgen05 single pass (11-bit mantissa operands, fp32 accumulate); "mma": warp-level m16n8k8
+# tensor-core MMAs with the same big+small split (fp32-class) for the decoder; "mma_tf32": the same, single pass
+CONV_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2, "mma": 3, "mma_tf32": 4}
 
 
 class _PositionCode(nn.Module):
@@ -86,7 +87,7 @@ class GRUUNet2(nn.Module):
         self.latent_size = hidden_sizes[-1]
         self.num_compressed_bins = num_compressed_bins
         self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
-        self.conv_mode = "fp32"  # one of CONV_MODES
+        self.conv_mode = "mma"  # one of CONV_MODES (default: tensor-core MMAs with the fp32-class big+small TF32 split)
         self._native = None  # (signature, handle, finalizer)
         self._ws = Workspace()
 

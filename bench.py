@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
-    ap.add_argument("--conv-mode", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--conv-mode", default="mma", choices=["fp32", "tf32x3", "tf32", "mma", "mma_tf32"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="clips per CPU-baseline pass (256 = the whole batch, ~4 s of host time per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")

@@ -106,7 +106,8 @@ int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* m
  * x [B, T, n_mels], hx [B, hidden, bins] in/out (caller zero-fills it for hx=None), out [B, T, n_mels].
  * Runs encoder (time-parallel) -> persistent recurrence -> decoder (time-parallel).
  * conv_mode: 0 = fp32 CUDA-core convolutions, 1 = tcgen05/TMEM implicit GEMM with TF32 operands split into
- * big + small parts (3 MMAs per k-step, fp32-class accuracy), 2 = tcgen05 single-pass TF32 (throughput mode).
+ * big + small parts (3 MMAs per k-step, fp32-class accuracy), 2 = tcgen05 single-pass TF32 (throughput mode),
+ * 3 = decoder on warp-level m16n8k8 tensor-core MMAs with the same big + small split (fp32-class), 4 = the same, single pass.
  * In the fused chains conv_mode != 0 also runs the inverse-mel projection as a tcgen05 GEMM. */
 size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T);
 int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T,

@@ -437,9 +437,10 @@ def test_rand_init_draws_are_uniform(dev):
 
 
 # ---------------------------------------------------------------------------------------------- tcgen05 path
-@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-5), ("tf32", 5e-3), ("mma", 1e-5), ("mma_tf32", 5e-3)])
 def test_model_tensor_core_modes(dev, golden, mode, tol):
-    """conv_mode tf32x3 / tf32: encoder + decoder as tcgen05/TMEM implicit GEMMs (conv_tc.cu)."""
+    """conv_mode tf32x3 / tf32: encoder + decoder as tcgen05/TMEM implicit GEMMs (conv_tc.cu); mma / mma_tf32: the
+    decoder on warp-level m16n8k8 tensor-core MMAs (unet_mma.cu)."""
     _, metrics, model, *_ = _oracle()
     z = golden("model_io.npz")
     x = torch.from_numpy(z["x"]).to(dev)
@@ -464,14 +465,15 @@ def test_model_tensor_core_modes(dev, golden, mode, tol):
     assert metrics.rel_l2(y.cpu(), ry) < tol and metrics.rel_l2(h.cpu(), rh) < tol
 
 
-def test_pipeline_tensor_core_mode_within_budget(dev):
-    """Whole chain with conv_mode tf32x3 (incl. the tcgen05 inverse-mel GEMM): same 0.05 dB SI-SDR budget."""
+@pytest.mark.parametrize("mode", ["tf32x3", "mma"])
+def test_pipeline_tensor_core_mode_within_budget(dev, mode):
+    """Whole chain with conv_mode tf32x3 / mma (incl. the tcgen05 inverse-mel GEMM): same 0.05 dB SI-SDR budget."""
     import audio_denoising_b200 as adb
 
     dsp, metrics, model, pipeline, synth = _oracle()
     noisy, clean = synth.make_batch(4, 16000, 16000, start=80)
     m, sd, cfg = _our_model("good", dev)
-    m.conv_mode = "tf32x3"
+    m.conv_mode = mode
     T = 1 + 16000 // 512
     init = synth.gl_init_angles((4, 513, T), seed=7)
     ref = pipeline.denoise_batch(noisy, model.GRUUNet2Oracle(sd, cfg), 1024, 512, 64, 16000, 32, 0.99, init)

@@ -17,6 +17,7 @@ warm = 100
 dev = torch.device("cuda:0")
 sd, cfg = load_weights("dari_tult2")
 m = adb.GRUUNet2(**cfg); m.load_state_dict(sd); m = m.to(dev).eval()
+m.conv_mode = os.environ.get('CONV_MODE', m.conv_mode)
 rows = []
 for sr, n_fft, hop in [(16000, 640, 320), (48000, 1536, 768), (16000, 1024, 512)]:
     for S in (1, 64):
@@ -32,7 +33,7 @@ for sr, n_fft, hop in [(16000, 640, 320), (48000, 1536, 768), (16000, 1024, 512)
             if i >= warm:
                 lat.append(dt * 1e3)
         lat = np.array(lat)
-        row = dict(sr=sr, n_fft=n_fft, hop=hop, hop_ms=1000.0 * hop / sr, sessions=S, hops=hops,
+        row = dict(conv_mode=m.conv_mode, sr=sr, n_fft=n_fft, hop=hop, hop_ms=1000.0 * hop / sr, sessions=S, hops=hops,
                    p50_ms=round(float(np.percentile(lat, 50)), 4), p99_ms=round(float(np.percentile(lat, 99)), 4),
                    mean_ms=round(float(lat.mean()), 4), realtime_factor=round(1000.0 * hop / sr / float(np.percentile(lat, 50)), 1))
         rows.append(row)
