@@ -14,10 +14,26 @@ __global__ void __launch_bounds__(256) peak_partial_kernel(const float* __restri
                                                            float* __restrict__ partial) {
   const int b = blockIdx.y;
   const float* x = wave + (size_t)b * L;
-  const int per = (L + chunks - 1) / chunks;
-  const int lo = blockIdx.x * per, hi = min(L, lo + per);
+  const int per = ((L + chunks - 1) / chunks + 3) & ~3;
+  const int lo = min(L, (int)blockIdx.x * per), hi = min(L, lo + per);
   float m = 0.f;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  if ((((size_t)x) & 15) == 0) {  // 16-byte aligned clip row: float4 body, four loads in flight per thread
+    const float4* x4 = reinterpret_cast<const float4*>(x + lo);
+    const int n4 = (hi - lo) >> 2;
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
+      const float4 a = x4[i], b = x4[i + blockDim.x], c = x4[i + 2 * blockDim.x], d = x4[i + 3 * blockDim.x];
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))), fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    }
+    for (; i < n4; i += blockDim.x) {
+      const float4 a = x4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (int j = lo + 4 * n4 + threadIdx.x; j < hi; j += blockDim.x) m = fmaxf(m, fabsf(x[j]));
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  }
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ float s[8];
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;

@@ -633,3 +633,21 @@ def test_resample_round_trip_44k1_48k(dev):
     assert y.shape[-1] == 44100
     mid = slice(400, 43700)  # away from the zero-padded edges
     assert (y[mid] - x[mid]).abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 64001), (5, 7), (1, 16384), (4, 16390), (2, 1)])
+def test_peak_is_exact(dev, B, L):
+    """K0 (app3.py:181-186): max |x| per clip, exact for every alignment / tail length; silence maps to 1."""
+    from audio_denoising_b200 import _cabi
+
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    x = torch.randn(B, L, generator=g)
+    x[0] *= 0.0  # digital silence -> peak 1 (no division by zero downstream)
+    if B > 1:
+        x[1, L - 1] = -7.5  # the maximum sits in the last (possibly unaligned) sample
+    xd = x.to(dev)
+    peak = torch.empty(B, device=dev)
+    _cabi.check(_cabi.lib().b2d_peak(xd.data_ptr(), B, L, peak.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    want = x.abs().amax(dim=1)
+    want = torch.where(want > 1e-6, want, torch.ones_like(want))
+    assert torch.equal(peak.cpu(), want)
