@@ -266,7 +266,9 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
     // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
     const int wps = q.fast == 3 ? gl_fast_n2048_warps() : gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
-    const int maxR = (T + 3) / 4;  // at least 4 frames per run
+    const char* mn = getenv("B2D_GL_MIN_RUN");
+    const int min_run = mn ? (atoi(mn) < 1 ? 1 : atoi(mn)) : 2;  // frames per run: short runs cut the latency of small batches
+    const int maxR = (T + min_run - 1) / min_run;
     if (gl_fast_persistent() || q.fast >= 2) {
       // Measured: a warp needs ~4.5 us per frame whether 1 or 12 warps share the SM (the kernel is latency-bound per
       // warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).  Minimise that; ties -> longer runs
