@@ -17,6 +17,7 @@ import torch
 
 from . import _cabi
 from ._runtime import Workspace, draw_seed, get_plan, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
+from .transforms import float_to_pcm16, pcm16_to_float
 from .gruunet2 import CONV_MODES, GRUUNet2
 
 
@@ -119,11 +120,16 @@ class DenoisePipeline:
         """
         if noisy_host.is_cuda:
             raise ValueError("denoise_host takes host tensors; use denoise() for device tensors")
+        pcm = noisy_host.dtype == torch.int16  # int16 PCM in -> int16 PCM out (app3.py:168-172 / 244-245), half the link bytes
+        if not pcm and noisy_host.dtype != torch.float32:
+            raise TypeError("denoise_host takes float32 waveforms or int16 PCM")
         B, L = noisy_host.shape
         T = self.plan.num_frames(L)
         Lout = self.plan.out_length(T)
         if out_host is None:
-            out_host = torch.empty((B, Lout), dtype=torch.float32, pin_memory=True)
+            out_host = torch.empty((B, Lout), dtype=noisy_host.dtype, pin_memory=True)
+        elif out_host.dtype != noisy_host.dtype:
+            raise TypeError("out_host must have the dtype of noisy_host")
         dev = self.device
         chunks = max(1, min(chunks, B))
         bounds = [(i * B) // chunks for i in range(chunks + 1)]
@@ -139,7 +145,12 @@ class DenoisePipeline:
                 ev_in.record(h2d)
             compute.wait_event(ev_in)
             ia = None if init_angles is None else init_angles[lo:hi]
-            wave, _ = self.denoise(xin, init_angles=ia, rand_init=rand_init)
+            if pcm:
+                xf = pcm16_to_float(xin.reshape(-1)).reshape(xin.shape)
+                wave, _ = self.denoise(xf, init_angles=ia, rand_init=rand_init)
+                wave = float_to_pcm16(wave)
+            else:
+                wave, _ = self.denoise(xin, init_angles=ia, rand_init=rand_init)
             xin.record_stream(compute)
             ev_done = torch.cuda.Event()
             ev_done.record(compute)

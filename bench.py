@@ -201,6 +201,9 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from audio_denoising_b200.sharding import bind_host_to_gpu
+
+    numa = bind_host_to_gpu(local)  # before any pinned allocation: staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     adb.native_library()
@@ -316,6 +319,28 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * SECONDS / float(t2.item())
+    # the same with int16 PCM on the link (what app3.py's recv exchanges, app3.py:168-172 / 244-245): conversions run on the GPU
+    pcm_in = [(h.clamp(-1, 1) * 32767).to(torch.int16).pin_memory() for h in host_in]
+    pcm_out = [torch.empty((B, Lout), dtype=torch.int16, pin_memory=True) for _ in range(2)]
+    for i in range(3):
+        pipe.denoise_host(pcm_in[i % 2], pcm_out[i % 2], wait=False)
+    pipe.host_synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pipe.denoise_host(pcm_in[i % 2], pcm_out[i % 2], wait=False)
+    pipe.host_synchronize()
+    t3 = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    e2e_pcm16 = world * B * SECONDS / float(t3.item())
+    if os.environ.get("B2D_BENCH_DEBUG"):
+        for tag, (hi_, ho_) in {"fp32-again": (host_in, host_out), "pcm-again": (pcm_in, pcm_out)}.items():
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                pipe.denoise_host(hi_[i % 2], ho_[i % 2], wait=False)
+            pipe.host_synchronize()
+            print(f"[debug] {tag}: {(time.perf_counter() - t0) / e2e_steps * 1e3:.3f} ms/step; first fp32 {e2e_s * 1e3:.3f}", file=sys.stderr, flush=True)
     # host link bandwidth seen by this process (explains e2e when the PCIe link, not the kernels, is the limit)
     def copy_gbs(dst, src):
         torch.cuda.synchronize(dev)
@@ -348,7 +373,8 @@ def run_b200(args):
                        "l2": "per-step working set ~0.6 GB >> 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * Lout * 4,
-                    "steps": e2e_steps, "pipelined": True, **link},
+                    "steps": e2e_steps, "pipelined": True, **link, "host_numa_binding": numa,
+                    "int16_pcm_io": {"value": round(e2e_pcm16, 1), "h2d_bytes_per_step": B * L * 2, "d2h_bytes_per_step": B * Lout * 2}},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -652,3 +652,24 @@ def test_peak_is_exact(dev, B, L):
     want = x.abs().amax(dim=1)
     want = torch.where(want > 1e-6, want, torch.ones_like(want))
     assert torch.equal(peak.cpu(), want)
+
+
+def test_denoise_host_pcm16_matches_float_path(dev):
+    """Host-to-host with int16 PCM on the link == int16 conversion around the float32 path (same injected initial phase)."""
+    import audio_denoising_b200 as adb
+
+    *_, synth = _oracle()
+    noisy, _ = synth.make_batch(3, 16000, 16000, start=120)
+    noisy = noisy / noisy.abs().amax(dim=1, keepdim=True) * 0.9
+    m, *_ = _our_model("good", dev)
+    pipe = adb.DenoisePipeline(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=16000)
+    T = 1 + 16000 // 512
+    init = synth.gl_init_angles((3, 513, T), seed=3).to(dev)
+    pcm = (noisy * 32767).to(torch.int16)
+    got = pipe.denoise_host(pcm.pin_memory(), init_angles=init)
+    assert got.dtype == torch.int16 and got.shape == (3, 512 * (T - 1))
+    ref = pipe.denoise_host((pcm.float() / 32767).pin_memory(), init_angles=init)
+    want = (ref.clamp(-1, 1) * 32767).to(torch.int16)
+    assert (got.int() - want.int()).abs().max() <= 1
+    with pytest.raises(TypeError):
+        pipe.denoise_host(torch.zeros(2, 16000, dtype=torch.float64).pin_memory())

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser(); ap.add_argument("--clips", type=int, default=100
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
+from audio_denoising_b200.sharding import bind_host_to_gpu
+numa = bind_host_to_gpu(local)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
 sd, cfg = bench.load_model_weights()
 m = adb.GRUUNet2(**cfg); m.load_state_dict(sd); m = m.to(dev).eval()
