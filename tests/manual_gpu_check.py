@@ -1,4 +1,4 @@
-"""First-contact GPU check: runs every stage against the oracle and prints the errors (no asserts)."""
+"""First-contact GPU check (run by hand: python tests/manual_gpu_check.py): every stage against the oracle, errors printed, no asserts."""
 import os, sys, time, json, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

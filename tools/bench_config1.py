@@ -9,22 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import audio_denoising_b200 as adb
-import bench
-from oracle import model as omodel, pipeline as opipe
+import bench  # the CPU leg is bench.py's own cpu_baseline code path (bench.cpu_pass_seconds): the oracle port, timed on the host cores
 
 L = 64000
 noisy = bench.synth_batch(1, L, seed=1234)
 sd, cfg = bench.load_model_weights()
-ref_model = omodel.GRUUNet2Oracle(sd, cfg)
 row = {"config": "1 clip x 4 s @ 16 kHz, n_fft 1024, hop 512, 64 mels, GL 32 it (BASELINE configs[0])", "cpu_count": os.cpu_count()}
 for threads in (1, os.cpu_count()):
-    torch.set_num_threads(threads)
-    opipe.denoise_batch(noisy, ref_model, 1024, 512, 64, 16000, 32, 0.99, None)
-    best = 1e9
-    for _ in range(5):
-        t0 = time.perf_counter()
-        opipe.denoise_batch(noisy, ref_model, 1024, 512, 64, 16000, 32, 0.99, None)
-        best = min(best, time.perf_counter() - t0)
+    best = bench.cpu_pass_seconds(1, 5, threads)
     row[f"cpu_{threads}_threads_ms"] = round(best * 1e3, 2)
     row[f"cpu_{threads}_threads_audio_s_per_s"] = round(4.0 / best, 1)
 dev = torch.device("cuda:0")

@@ -4,12 +4,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import audio_denoising_b200 as adb
-from oracle import model as omodel
+import bench
 
 dev = torch.device("cuda:0")
 B, T = 256, 126
-m = adb.GRUUNet2(**omodel.default_config())
-m.load_state_dict(omodel.random_state_dict(seed=3))
+sd, cfg = bench.load_model_weights()
+m = adb.GRUUNet2(**cfg)
+m.load_state_dict(sd)
 m = m.to(dev)
 x = torch.rand(B, T, 64, device=dev) * 3
 ref = None
