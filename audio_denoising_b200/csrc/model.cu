@@ -219,12 +219,15 @@ __global__ void __launch_bounds__(ENC2_WARPS * 32, 2) encoder2_kernel(const floa
 // recurrence: one CTA (96 threads, 68 active) per clip; thread (c, j) owns hidden channel c at
 // compressed bin j and keeps its 3 x 17 x 3 recurrent weights in registers for all T steps.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Gate non-linearities on the exp2 unit (ex2.approx has 2 ulp of error, the reciprocal 1 ulp: ~3e-7 relative, far inside
+// the 1e-5 model parity budget); tanh(v) = 1 - 2 / (1 + e^{2v}) saturates cleanly to +-1 when the exponential overflows / underflows.
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
 
 __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict__ blob, const float* __restrict__ gx,
                                                         float* __restrict__ hx, float* __restrict__ hseq, int T) {
   const Packed L = packed_layout();
-  __shared__ float hp[H][BINS + 2];  // zero padded at both ends
+  __shared__ float hp[2][H][BINS + 2];  // double-buffered hidden state, zero padded at both ends: one barrier per step
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const bool active = tid < H * BINS;
@@ -242,12 +245,12 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
       pb[g] = blob[L.rec_pb + (g * H + c) * BINS + j];
     }
   }
-  for (int i = tid; i < H * (BINS + 2); i += blockDim.x) (&hp[0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * H * (BINS + 2); i += blockDim.x) (&hp[0][0][0])[i] = 0.f;
   __syncthreads();
   float h = 0.f;
   if (active) {
     h = hx[(size_t)b * HS + c * BINS + j];
-    hp[c][j + 1] = h;
+    hp[0][c][j + 1] = h;
   }
   __syncthreads();
   const float* gxb = gx + (size_t)b * T * GX;
@@ -266,27 +269,28 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
       nz = g1[(H + c) * BINS + j];
       nn = g1[(2 * H + c) * BINS + j];
     }
-    float ar = pb[0], az = pb[1], an = pb[2];
+    // three partial sums per gate (one per tap): dependency chains of 17 instead of 51 FMAs
+    const float (*hc)[BINS + 2] = hp[t & 1];
+    float ar[3] = {pb[0], 0.f, 0.f}, az[3] = {pb[1], 0.f, 0.f}, an[3] = {pb[2], 0.f, 0.f};
 #pragma unroll
     for (int ci = 0; ci < H; ++ci) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float v = hp[ci][j + k];
-        ar = fmaf(w[0][ci][k], v, ar);
-        az = fmaf(w[1][ci][k], v, az);
-        an = fmaf(w[2][ci][k], v, an);
+        const float v = hc[ci][j + k];
+        ar[k] = fmaf(w[0][ci][k], v, ar[k]);
+        az[k] = fmaf(w[1][ci][k], v, az[k]);
+        an[k] = fmaf(w[2][ci][k], v, an[k]);
       }
     }
-    ar = fmaxf(ar, 0.f);  // both pre-activations went through ReLU (gruunet2.py:71-79, Q8)
-    az = fmaxf(az, 0.f);
-    an = fmaxf(an, 0.f);
-    const float z = sigmoidf_(xz + az);
-    const float r = sigmoidf_(xr + ar);
-    const float nw = tanhf(xn + r * an);
+    const float sr = fmaxf(ar[0] + ar[1] + ar[2], 0.f);  // both pre-activations went through ReLU (gruunet2.py:71-79, Q8)
+    const float sz = fmaxf(az[0] + az[1] + az[2], 0.f);
+    const float sn = fmaxf(an[0] + an[1] + an[2], 0.f);
+    const float z = sigmoidf_(xz + sz);
+    const float r = sigmoidf_(xr + sr);
+    const float nw = tanhf_(xn + r * sn);
     const float hn = nw + z * (h - nw);
-    __syncthreads();  // everyone has read hp for this step
     if (active) {
-      hp[c][j + 1] = hn;
+      hp[(t + 1) & 1][c][j + 1] = hn;  // the other buffer: nobody reads it during this step
       hsb[(size_t)t * HS + c * BINS + j] = hn;
     }
     h = hn;
