@@ -285,8 +285,16 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
         const int Reff = (T + n - 1) / n;
         const long runs = (long)B * Reff;
         const long rounds = (runs + slots - 1) / slots;
-        const long cost = rounds * (q.fast == 2 ? n / 2 : n);
+        const long cost = rounds * ((q.fast == 2 ? n / 2 : n) + 1);  // + 1: a run's fixed cost (first rows, boundary blocks, carry flush)
         if (best < 0 || cost < best) { best = cost; bestR = Reff; bestN = n; }
+      }
+      if (const char* fn = getenv("B2D_GL_RUN")) {  // experiments: force the run length
+        int n = atoi(fn);
+        if (n >= 1 && n <= T) {
+          if (q.fast == 2) n = (n + 1) & ~1;
+          bestN = n;
+          bestR = (T + n - 1) / n;
+        }
       }
       q.n = bestN;
       q.R = bestR;
