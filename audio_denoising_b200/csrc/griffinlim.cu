@@ -277,6 +277,11 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
       //  n = 20, R = 7 for config 2 -- every slot busy, 20 frames on the busiest instead of 21 -- and is 3.7 % slower; the
       //  reordered schedule alone costs 3-5 %: with all slots busy the launch is throughput-bound, the extra run boundary
       //  per clip costs traffic, and runs of one clip that are not walked at the same time lose their shared hop-blocks in L2.)
+      // (Second measured dead end: a balanced run table -- the flattened B x T frames cut into 1776 equal shares of 18-19
+      //  frames, split at clip boundaries, runs stored back to back so boundary partial sums are adjacent blocks -- was
+      //  correct but slower: 97.5 us instead of 88.4 us at B = 256, 375 instead of 310 us at B = 1024.  Filling every warp slot
+      //  does not help because 1536 busy warps already saturate the SMs' issue / shared-memory throughput; it only adds
+      //  run boundaries and table look-ups at the head of every run.)
       long best = -1; int bestR = 1;
       int bestN = T;
       for (int R = 1; R <= maxR; ++R) {
