@@ -134,30 +134,49 @@ class DenoisePipeline:
         chunks = max(1, min(chunks, B))
         bounds = [(i * B) // chunks for i in range(chunks + 1)]
         if self._host is None:
-            self._host = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev))
+            self._host = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), slots={}, turn={})
         h2d, d2h = self._host["h2d"], self._host["d2h"]
         compute = torch.cuda.current_stream(dev)
         for i in range(chunks):
             lo, hi = bounds[i], bounds[i + 1]
+            # Device staging is allocated once per shape and double-buffered (slot = two tensors + the events that say when
+            # they are free again): nothing is allocated per call, so the caching allocator never has to synchronise streams.
+            key = (hi - lo, L, noisy_host.dtype)
+            ring = self._host["slots"].get(key)
+            if ring is None:
+                ring = [dict(xin=torch.empty((hi - lo, L), dtype=noisy_host.dtype, device=dev),
+                             wave=torch.empty((hi - lo, Lout), dtype=torch.float32, device=dev),
+                             in_free=None, out_free=None) for _ in range(2)]
+                self._host["slots"][key] = ring
+                self._host["turn"][key] = 0
+            slot = ring[self._host["turn"][key] & 1]
+            self._host["turn"][key] += 1
             with torch.cuda.stream(h2d):
-                xin = noisy_host[lo:hi].to(dev, non_blocking=True)
+                if slot["in_free"] is not None:
+                    h2d.wait_event(slot["in_free"])  # the kernels of two batches ago have consumed this input buffer
+                slot["xin"].copy_(noisy_host[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(h2d)
             compute.wait_event(ev_in)
+            if slot["out_free"] is not None:
+                compute.wait_event(slot["out_free"])  # ... and its result has left for the host
             ia = None if init_angles is None else init_angles[lo:hi]
             if pcm:
-                xf = pcm16_to_float(xin.reshape(-1)).reshape(xin.shape)
-                wave, _ = self.denoise(xf, init_angles=ia, rand_init=rand_init)
-                wave = float_to_pcm16(wave)
+                xf = pcm16_to_float(slot["xin"].reshape(-1)).reshape(slot["xin"].shape)
+                self.denoise(xf, init_angles=ia, rand_init=rand_init, out=slot["wave"])
+                result = float_to_pcm16(slot["wave"])
             else:
-                wave, _ = self.denoise(xin, init_angles=ia, rand_init=rand_init)
-            xin.record_stream(compute)
-            ev_done = torch.cuda.Event()
-            ev_done.record(compute)
+                self.denoise(slot["xin"], init_angles=ia, rand_init=rand_init, out=slot["wave"])
+                result = slot["wave"]
+            slot["in_free"] = torch.cuda.Event()
+            slot["in_free"].record(compute)
             with torch.cuda.stream(d2h):
-                d2h.wait_event(ev_done)
-                out_host[lo:hi].copy_(wave, non_blocking=True)
-                wave.record_stream(d2h)
+                d2h.wait_event(slot["in_free"])
+                out_host[lo:hi].copy_(result, non_blocking=True)
+                if pcm:
+                    result.record_stream(d2h)
+                slot["out_free"] = torch.cuda.Event()
+                slot["out_free"].record(d2h)
         if wait:
             self.host_synchronize()
         return out_host
