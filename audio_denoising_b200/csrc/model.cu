@@ -100,121 +100,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encoder_kernel(const float* __
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// encoder, register-tiled (same scheme as decoder2): a warp works on 2 frames; a lane owns one OUTPUT position of
-// one frame (and, in the small layers, a slice of the output channels) and keeps its accumulators in registers.
-// Per input channel: 3 activation loads, 3 broadcast float4 weight loads per channel group, 12 FMAs per group.
-// ------------------------------------------------------------------------------------------------
-constexpr int ENC2_WARPS = 8;
-constexpr int ENC2_FW = 2;
-constexpr int ENC2_FR = ENC_ACT + 12;  // 1232: the two frames of a warp land on different banks
-
-template <int CIN, int COUT, int COP, int LIN, int CSPLIT>
-__device__ __forceinline__ void enc2_layer(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ PB,
-                                           float* __restrict__ out, int j, int cs) {
-  constexpr int LOUT = LIN / 2;
-  constexpr int NG = COP / 4;
-  constexpr int NGL = (NG + CSPLIT - 1) / CSPLIT;
-  const int g0 = cs * NGL;
-  float4 acc[NGL];
-#pragma unroll
-  for (int gl = 0; gl < NGL; ++gl)
-    acc[gl] = ((CSPLIT == 1) || (g0 + gl < NG)) ? *reinterpret_cast<const float4*>(PB + j * COP + 4 * (g0 + gl)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool has_l = (j > 0), has_r = (2 * j + 1 < LIN);
-#pragma unroll 2
-  for (int ci = 0; ci < CIN; ++ci) {
-    const float* row = in + ci * LIN + 2 * j;
-    const float a0 = has_l ? row[-1] : 0.f;
-    const float a1 = row[0];
-    const float a2 = has_r ? row[1] : 0.f;
-    const float* w = W + ci * 3 * COP + 4 * g0;
-#pragma unroll
-    for (int gl = 0; gl < NGL; ++gl) {
-      if ((CSPLIT == 1) || (g0 + gl < NG)) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * gl);
-        const float4 w1 = *reinterpret_cast<const float4*>(w + COP + 4 * gl);
-        const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * COP + 4 * gl);
-        acc[gl].x = fmaf(a0, w0.x, fmaf(a1, w1.x, fmaf(a2, w2.x, acc[gl].x)));
-        acc[gl].y = fmaf(a0, w0.y, fmaf(a1, w1.y, fmaf(a2, w2.y, acc[gl].y)));
-        acc[gl].z = fmaf(a0, w0.z, fmaf(a1, w1.z, fmaf(a2, w2.z, acc[gl].z)));
-        acc[gl].w = fmaf(a0, w0.w, fmaf(a1, w1.w, fmaf(a2, w2.w, acc[gl].w)));
-      }
-    }
-  }
-#pragma unroll
-  for (int gl = 0; gl < NGL; ++gl) {
-    const float r[4] = {acc[gl].x, acc[gl].y, acc[gl].z, acc[gl].w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int co = 4 * (g0 + gl) + q;
-      if (co < COUT) out[co * LOUT + j] = fmaxf(r[q], 0.f);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(ENC2_WARPS * 32, 2) encoder2_kernel(const float* __restrict__ blob, const float* __restrict__ x,
-                                                                      size_t nframes, float* __restrict__ d0, float* __restrict__ d1,
-                                                                      float* __restrict__ d2, float* __restrict__ gx) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Packed L = packed_layout();
-  float* wts = reinterpret_cast<float*>(smem_raw);
-  const int nw = L.rec_w;
-  float* act = wts + ((nw + 3) & ~3);
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* base = act + warp * (ENC2_FW * ENC2_FR);
-  const size_t stride = (size_t)gridDim.x * ENC2_WARPS * ENC2_FW;
-  for (size_t f0 = ((size_t)blockIdx.x * ENC2_WARPS + warp) * ENC2_FW; f0 < nframes; f0 += stride) {
-    const int nf = (int)min((size_t)ENC2_FW, nframes - f0);
-    if (f0 + stride + ENC2_FW <= nframes) prefetch_l2_range(x + (f0 + stride) * NMEL, ENC2_FW * NMEL * 4, lane);
-    for (int f = 0; f < nf; ++f) {
-      float* a_in = base + f * ENC2_FR;
-      a_in[lane] = x[(f0 + f) * NMEL + lane];
-      a_in[lane + 32] = x[(f0 + f) * NMEL + lane + 32];
-    }
-    __syncwarp();
-    for (int f = 0; f < nf; ++f) {  // L0: [1][64] -> [17][32]   one frame per pass
-      float* a_in = base + f * ENC2_FR;
-      enc2_layer<1, H, HP, 64, 1>(a_in, wts + L.enc_w[0], wts + L.enc_pb[0], a_in + NMEL, lane, 0);
-    }
-    __syncwarp();
-    {  // L1: [17][32] -> [17][16]   lane = f*16 + j
-      const int f = lane >> 4, j = lane & 15;
-      if (f < nf) {
-        float* a0 = base + f * ENC2_FR + NMEL;
-        enc2_layer<H, H, HP, 32, 1>(a0, wts + L.enc_w[1], wts + L.enc_pb[1], a0 + D0, j, 0);
-      }
-    }
-    __syncwarp();
-    {  // L2: [17][16] -> [17][8]    lane = f*16 + j*2 + channel split
-      const int f = lane >> 4, j = (lane >> 1) & 7, cs = lane & 1;
-      if (f < nf) {
-        float* a1 = base + f * ENC2_FR + NMEL + D0;
-        enc2_layer<H, H, HP, 16, 2>(a1, wts + L.enc_w[2], wts + L.enc_pb[2], a1 + D1, j, cs);
-      }
-    }
-    __syncwarp();
-    {  // L3: [17][8] -> [51][4]     lane = f*16 + j*4 + channel split (13 groups over 4 lanes)
-      const int f = lane >> 4, j = (lane >> 2) & 3, cs = lane & 3;
-      if (f < nf) {
-        float* a2 = base + f * ENC2_FR + NMEL + D0 + D1;
-        enc2_layer<H, H3, H3P, 8, 4>(a2, wts + L.enc_w[3], wts + L.enc_pb[3], a2 + D2, j, cs);
-      }
-    }
-    __syncwarp();
-    for (int f = 0; f < nf; ++f) {
-      const float* a0 = base + f * ENC2_FR + NMEL;
-      const size_t fr = f0 + f;
-      for (int i = lane; i < D0; i += 32) d0[fr * D0 + i] = a0[i];
-      for (int i = lane; i < D1; i += 32) d1[fr * D1 + i] = a0[D0 + i];
-      for (int i = lane; i < D2; i += 32) d2[fr * D2 + i] = a0[D0 + D1 + i];
-      for (int i = lane; i < GX; i += 32) gx[fr * GX + i] = a0[D0 + D1 + D2 + i];
-    }
-    __syncwarp();
-  }
-}
-
+// (A register-tiled variant of this encoder -- a lane owning one output position of one frame, same scheme as the
+//  decoder below -- measured 25 us slower: both are bound by the shared-memory weight loads.  The default encoder is the
+//  tensor-core one in unet_mma.cu; this kernel is conv_mode "fp32".)
 // ------------------------------------------------------------------------------------------------
 // recurrence: one CTA (96 threads, 68 active) per clip; thread (c, j) owns hidden channel c at
 // compressed bin j and keeps its 3 x 17 x 3 recurrent weights in registers for all T steps.
@@ -301,104 +189,10 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// decoder: one warp per frame.  ConvTranspose1d(k3,s2,p1,op1):
+// decoder (conv_mode "fp32"; the default is the tensor-core decoder in unet_mma.cu).  ConvTranspose1d(k3,s2,p1,op1):
 //   out[co,2j]   = pb + sum_ci x[ci,j] W[ci,1,co]
 //   out[co,2j+1] = pb + sum_ci (x[ci,j] W[ci,2,co] + x[ci,j+1] W[ci,0,co])
-// ------------------------------------------------------------------------------------------------
-template <int CIN, int COP, int LIN, bool RELU>
-__device__ __forceinline__ void dec_layer(const float* __restrict__ in, const float* __restrict__ W,
-                                          const float* __restrict__ PB, float* __restrict__ out, int cout, int lane) {
-  constexpr int LOUT = LIN * 2;
-  constexpr int NG = COP / 4;
-  for (int item = lane; item < LOUT * NG; item += 32) {
-    const int o = item % LOUT, cg = item / LOUT;
-    const int j = o >> 1;
-    const bool odd = o & 1;
-    float4 acc = *reinterpret_cast<const float4*>(PB + o * COP + cg * 4);
-#pragma unroll 6
-    for (int ci = 0; ci < CIN; ++ci) {
-      const float* row = in + ci * LIN;
-      const float v0 = row[j];
-      const float4 w0 = *reinterpret_cast<const float4*>(W + (ci * 3 + (odd ? 2 : 1)) * COP + cg * 4);
-      acc.x = fmaf(v0, w0.x, acc.x);
-      acc.y = fmaf(v0, w0.y, acc.y);
-      acc.z = fmaf(v0, w0.z, acc.z);
-      acc.w = fmaf(v0, w0.w, acc.w);
-      if (odd && j + 1 < LIN) {
-        const float v1 = row[j + 1];
-        const float4 w1 = *reinterpret_cast<const float4*>(W + (ci * 3 + 0) * COP + cg * 4);
-        acc.x = fmaf(v1, w1.x, acc.x);
-        acc.y = fmaf(v1, w1.y, acc.y);
-        acc.z = fmaf(v1, w1.z, acc.z);
-        acc.w = fmaf(v1, w1.w, acc.w);
-      }
-    }
-    float r[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int co = cg * 4 + q;
-      if (co < cout) out[co * LOUT + o] = RELU ? fmaxf(r[q], 0.f) : r[q];
-    }
-  }
-}
-
-constexpr int DEC_WARPS = 8;
-// per-warp activations: u0 [34][4->8]: stage inputs are [2H][L] with rows 0..H-1 = upsampled, H..2H-1 = skip
-constexpr int DEC_ACT = H * 4 + 2 * H * 8 + 2 * H * 16 + 2 * H * 32 + 64;
-
-__global__ void __launch_bounds__(DEC_WARPS * 32) decoder_kernel(const float* __restrict__ blob, const float* __restrict__ hseq,
-                                                                 const float* __restrict__ d0, const float* __restrict__ d1,
-                                                                 const float* __restrict__ d2, const float* __restrict__ x,
-                                                                 size_t nframes, float* __restrict__ pred,
-                                                                 float* __restrict__ mel, int fused_mode, float out_scale) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Packed L = packed_layout();
-  float* wts = reinterpret_cast<float*>(smem_raw);
-  const int w0 = L.dec_w[0];
-  const int nw = L.total - w0;
-  float* act = wts + ((nw + 3) & ~3);
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) wts[i] = blob[w0 + i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s0 = act + warp * DEC_ACT;  // [H][4]
-  float* s1 = s0 + H * 4;            // [2H][8]
-  float* s2 = s1 + 2 * H * 8;        // [2H][16]
-  float* s3 = s2 + 2 * H * 16;       // [2H][32]
-  float* s4 = s3 + 2 * H * 32;       // [1][64]
-  for (size_t f = (size_t)blockIdx.x * DEC_WARPS + warp; f < nframes; f += (size_t)gridDim.x * DEC_WARPS) {
-    for (int i = lane; i < HS; i += 32) s0[i] = hseq[f * HS + i];
-    for (int i = lane; i < D2; i += 32) s1[H * 8 + i] = d2[f * D2 + i];
-    for (int i = lane; i < D1; i += 32) s2[H * 16 + i] = d1[f * D1 + i];
-    for (int i = lane; i < D0; i += 32) s3[H * 32 + i] = d0[f * D0 + i];
-    __syncwarp();
-    dec_layer<H, HP, 4, true>(s0, wts + (L.dec_w[0] - w0), wts + (L.dec_pb[0] - w0), s1, H, lane);
-    __syncwarp();
-    dec_layer<2 * H, HP, 8, true>(s1, wts + (L.dec_w[1] - w0), wts + (L.dec_pb[1] - w0), s2, H, lane);
-    __syncwarp();
-    dec_layer<2 * H, HP, 16, true>(s2, wts + (L.dec_w[2] - w0), wts + (L.dec_pb[2] - w0), s3, H, lane);
-    __syncwarp();
-    dec_layer<2 * H, 4, 32, false>(s3, wts + (L.dec_w[3] - w0), wts + (L.dec_pb[3] - w0), s4, 1, lane);
-    __syncwarp();
-    for (int i = lane; i < NMEL; i += 32) {
-      const float p = s4[i];
-      pred[f * NMEL + i] = p;
-      if (fused_mode) {
-        const float xv = x[f * NMEL + i];
-        float v;
-        if (fused_mode == 1) {
-          float r = xv - p;
-          r = r > 0.f ? r : 0.2f * r;
-          v = fmaxf(expm1f(r), 0.f);
-        } else {
-          v = expf(xv - fmaxf(p, 0.f) * out_scale) - 1.0f;
-        }
-        mel[f * NMEL + i] = v;
-      }
-    }
-    __syncwarp();
-  }
-}
-
+// (The first version -- one warp per frame, work item = (output position, 4 output channels) -- took 655 us.)
 // ------------------------------------------------------------------------------------------------
 // (Measured dead end, kept as a note: passing the 27.5 KB decoder weights as a __grid_constant__ kernel parameter so that
 //  FMAs take warp-uniform constant operands was slower -- register-indexed LDC.64 when partially unrolled (+0.4 ms), and
@@ -722,22 +516,14 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   float* dec_scratch = reinterpret_cast<float*>(base);
   const Packed L = packed_layout();
   int dev_sms = 148;
+  if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess || dev_sms < 1) dev_sms = 148;
   if (fma_encoder) {
-    if (getenv("B2D_ENCODER_V2") == nullptr) {  // v1 measures 25 us faster: both are bound by shared-memory weight loads
-      const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
-      B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
-      const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
-      encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
-      B2D_LAUNCH_CHECK("encoder_kernel");
-    } else {
-      const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC2_WARPS * ENC2_FW * ENC2_FR);
-      B2D_CUDA(cudaFuncSetAttribute(encoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const size_t want = (nf + ENC2_WARPS * ENC2_FW - 1) / (ENC2_WARPS * ENC2_FW);
-      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
-      encoder2_kernel<<<grid, ENC2_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
-      B2D_LAUNCH_CHECK("encoder2_kernel");
-    }
+    const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
+    B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
+    const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
+    encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
+    B2D_LAUNCH_CHECK("encoder_kernel");
   } else if (conv_mode >= 3) {
     int rc = model_encode_mma(m, x, nf, d0, d1, d2, gx, conv_mode == 3 ? 3 : 1, dev_sms, st);
     if (rc != B2D_OK) return rc;
@@ -752,21 +538,12 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
     if (rc != B2D_OK) return rc;
   } else if (conv_mode == 0) {
     const int nw = L.total - L.dec_w[0];
-    if (getenv("B2D_DECODER_V1")) {
-      const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC_WARPS * DEC_ACT);
-      B2D_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const size_t want = (nf + DEC_WARPS - 1) / DEC_WARPS;
-      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
-      decoder_kernel<<<grid, DEC_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
-      B2D_LAUNCH_CHECK("decoder_kernel");
-    } else {
-      const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC2_WARPS * DEC2_FW * DEC2_FR);
-      B2D_CUDA(cudaFuncSetAttribute(decoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const size_t want = (nf + DEC2_WARPS * DEC2_FW - 1) / (DEC2_WARPS * DEC2_FW);
-      const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
-      decoder2_kernel<<<grid, DEC2_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
-      B2D_LAUNCH_CHECK("decoder2_kernel");
-    }
+    const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC2_WARPS * DEC2_FW * DEC2_FR);
+    B2D_CUDA(cudaFuncSetAttribute(decoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t want = (nf + DEC2_WARPS * DEC2_FW - 1) / (DEC2_WARPS * DEC2_FW);
+    const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
+    decoder2_kernel<<<grid, DEC2_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
+    B2D_LAUNCH_CHECK("decoder2_kernel");
   } else {
     int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, dec_scratch, st);
     if (rc != B2D_OK) return rc;
