@@ -708,3 +708,29 @@ def test_fast_paths_match_generic_on_ragged_shapes(dev, monkeypatch, n_fft):
         # that for a few clips in a hundred, require > 100 dB for the typical one
         assert sdr.median() > 100.0 and sdr.min() > 30.0 and int((sdr <= 90.0).sum()) <= max(1, B // 10), \
             (n_fft, B, T, float(sdr.median()), float(sdr.min()))
+
+
+@pytest.mark.parametrize("n_fft,L,B", [(512, 16000, 2), (2048, 32000, 2), (1024, 160000, 2)])
+def test_pipeline_other_geometries_match_oracle(dev, n_fft, L, B):
+    """Whole chain vs the oracle for the other Griffin-Lim fast paths (n_fft 512 / 2048) and for the corpus geometry of
+    BASELINE config 4 (10 s clips, T = 313), same injected initial phase."""
+    import audio_denoising_b200 as adb
+
+    dsp, metrics, model, pipeline, synth = _oracle()
+    hop = n_fft // 2
+    noisy, clean = synth.make_batch(B, L, 16000, start=140)
+    m, sd, cfg = _our_model("good", dev)
+    T = 1 + L // hop
+    init = synth.gl_init_angles((B, n_fft // 2 + 1, T), seed=11)
+    ref = pipeline.denoise_batch(noisy, model.GRUUNet2Oracle(sd, cfg), n_fft, hop, 64, 16000, 32, 0.99, init)
+    pipe = adb.DenoisePipeline(m, n_fft=n_fft, hop_length=hop, n_mels=64, sample_rate=16000)
+    r = pipe.denoise(noisy.to(dev), init_angles=init.to(dev), return_intermediates=True)
+    assert metrics.rel_l2(r["logmel"].cpu(), ref["logmel"]) < 1e-4
+    assert metrics.rel_l2(r["pred"].cpu(), ref["pred"]) < 2e-5
+    assert metrics.rel_l2(r["lin_mag"].cpu(), ref["lin_mag"]) < 5e-5
+    assert r["wave"].shape == ref["wave"].shape
+    Lout = r["wave"].shape[1]
+    a = metrics.si_sdr(r["wave"].cpu(), clean[:, :Lout])
+    b = metrics.si_sdr(ref["wave"], clean[:, :Lout])
+    assert (a - b).abs().max() <= 0.05, (a.tolist(), b.tolist())
+    assert metrics.si_sdr(r["wave"].cpu(), ref["wave"]).min() >= 40.0
