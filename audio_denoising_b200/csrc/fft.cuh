@@ -12,6 +12,16 @@
 
 namespace b2d {
 
+// floor(n / d) for 0 <= n < 2^22 through the float unit: (n + 0.5) / d is never closer than 0.5 / d to an integer, far more
+// than the rounding error of the product, so the truncation is exact.  The kernels' index math (w / Q, j / Ns, idx / hop ...)
+// uses it instead of runtime integer division, which costs ~25 dependent instructions per quotient.
+struct FastDiv {
+  int d;
+  float inv;
+  B2D_HD FastDiv(int d_) : d(d_), inv(1.0f / (float)d_) {}
+  B2D_HD int div(int n) const { return (int)(((float)n + 0.5f) * inv); }
+};
+
 B2D_HD float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -151,10 +161,12 @@ template <bool INV, int R>
 B2D_HD void stockham_item(const float2* __restrict__ src, float2* __restrict__ dst, int w, int M, int ld, int Ns,
                           const float2* __restrict__ tw) {
   const int Q = M / R;
-  const int tstep = M / (Ns * R);
-  const int row = w / Q;
+  const FastDiv dq(Q), dn(Ns);
+  const int tstep = dn.div(Q);  // M / (Ns * R)
+  const int row = dq.div(w);
   const int j = w - row * Q;
-  const int k = j % Ns;
+  const int jq = dn.div(j);
+  const int k = j - jq * Ns;
   const float2* s = src + row * ld;
   float2* d = dst + row * ld;
   float2 v[R];
@@ -172,7 +184,7 @@ B2D_HD void stockham_item(const float2* __restrict__ src, float2* __restrict__ d
   if (R == 4) dft4<INV>(v);
   if (R == 5) dft5<INV>(v);
   if (R == 8) dft8<INV>(v);
-  const int j0 = (j / Ns) * Ns * R + k;
+  const int j0 = jq * Ns * R + k;
 #pragma unroll
   for (int q = 0; q < R; ++q) d[j0 + q * Ns] = v[q];
 }

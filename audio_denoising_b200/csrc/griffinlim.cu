@@ -50,20 +50,25 @@ struct GlArgs {
 // (`part` is deliberately not __restrict__: in fused mode the same launch wrote it one step earlier, so the loads must
 //  stay on the coherent path rather than ld.global.nc)
 __device__ __forceinline__ float x_block_sample(const float* part, const float* __restrict__ inv_env,
-                                                int b, int R, int n, int hop, int j, int i) {
-  const int r1 = (j - 1) / n, r2 = j / n;
+                                                int b, int R, const FastDiv& dn, int hop, int j, int i) {
+  const int n = dn.d;
+  const int r1 = dn.div(j - 1), r2 = dn.div(j);
   float v = part[((size_t)(b * R + r1) * (n + 1) + (j - r1 * n)) * hop + i];
   if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * hop + i];
   return v * inv_env[i];
 }
+__device__ __forceinline__ float x_block_sample(const float* part, const float* __restrict__ inv_env,
+                                                int b, int R, int n, int hop, int j, int i) {
+  return x_block_sample(part, inv_env, b, R, FastDiv(n), hop, j, i);
+}
 // sample i of padded hop-block j (0 <= j <= T) of the reflect-padded iterate
 __device__ __forceinline__ float x_padded(const float* part, const float* __restrict__ inv_env, int b,
-                                          int R, int n, int hop, int T, int j, int i) {
-  if (j == 0) return (i == 0) ? x_block_sample(part, inv_env, b, R, n, hop, 2, 0)
-                              : x_block_sample(part, inv_env, b, R, n, hop, 1, hop - i);
-  if (j == T) return (i == hop - 1) ? x_block_sample(part, inv_env, b, R, n, hop, T - 2, hop - 1)
-                                    : x_block_sample(part, inv_env, b, R, n, hop, T - 1, hop - 2 - i);
-  return x_block_sample(part, inv_env, b, R, n, hop, j, i);
+                                          int R, const FastDiv& dn, int hop, int T, int j, int i) {
+  if (j == 0) return (i == 0) ? x_block_sample(part, inv_env, b, R, dn, hop, 2, 0)
+                              : x_block_sample(part, inv_env, b, R, dn, hop, 1, hop - i);
+  if (j == T) return (i == hop - 1) ? x_block_sample(part, inv_env, b, R, dn, hop, T - 2, hop - 1)
+                                    : x_block_sample(part, inv_env, b, R, dn, hop, T - 1, hop - 2 - i);
+  return x_block_sample(part, inv_env, b, R, dn, hop, j, i);
 }
 
 __device__ __forceinline__ float2 unit_dir(float2 a) {
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
   for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = 0.f;
   __syncthreads();
   const int half = M / 2 + 1;
+  const FastDiv d_hop(hop), d_M(M), d_half(half), d_G(G), d_n(n);  // index math without integer division (fft.cuh)
   const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
   const int last_step = a.fused_iters >= 0 ? a.fused_iters : 0;
   const float* cur_in = a.xin;
@@ -118,12 +124,13 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
         __syncthreads();
       }
       for (int idx = threadIdx.x; idx < (gv + 1 - first) * hop; idx += blockDim.x) {
-        const int c = first + idx / hop, i = idx % hop;
-        xin_s[c * hop + i] = x_padded(cur_in, a.inv_env, b, R, n, hop, T, tb + c, i);
+        const int cq = d_hop.div(idx);
+        const int c = first + cq, i = idx - cq * hop;
+        xin_s[c * hop + i] = x_padded(cur_in, a.inv_env, b, R, d_n, hop, T, tb + c, i);
       }
       __syncthreads();
       for (int idx = threadIdx.x; idx < G * M; idx += blockDim.x) {
-        const int g = idx / M, m = idx - g * M;
+        const int g = d_M.div(idx), m = idx - g * M;
         float2 z = make_float2(0.f, 0.f);
         if (g < gv) {
           const float2 xv = *reinterpret_cast<const float2*>(xin_s + g * hop + 2 * m);
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       __syncthreads();
       float2* res = fft_rows<false>(bufA, bufB, G, M, a.fd, tw_s);
       for (int idx = threadIdx.x; idx < gv * half; idx += blockDim.x) {
-        const int g = idx / half, k = idx - g * half;
+        const int g = d_half.div(idx), k = idx - g * half;
         const int t = tb + g;
         const float2 zk = res[g * M + k];
         const float2 zmk = res[g * M + ((M - k) & -(k != 0))];
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       other = (res == bufA) ? bufB : bufA;
     } else {
       for (int idx = threadIdx.x; idx < G * half; idx += blockDim.x) {
-        const int k = idx / G, g = idx - k * G;
+        const int k = d_G.div(idx), g = idx - k * G;
         float2 z1 = make_float2(0.f, 0.f), z2 = z1;
         if (g < gv) {
           const int t = tb + g;
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
     float2* out = fft_rows<true>(src, other, G, M, a.fd, tw_s);
     const float* y = reinterpret_cast<const float*>(out);
     for (int idx = threadIdx.x; idx < gv * hop; idx += blockDim.x) {
-      const int c = idx / hop, i = idx - c * hop;
+      const int c = d_hop.div(idx), i = idx - c * hop;
       const float prev = (c == 0) ? carry_s[i] : y[(c - 1) * N + hop + i] * a.winn[hop + i];
       xo[(size_t)(tb - tbeg + c) * hop + i] = prev + y[c * N + i] * a.winn[i];
     }
