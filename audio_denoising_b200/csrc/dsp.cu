@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * G;
   const int p = N / 2;
+  const FastDiv d_M(M), d_half(M / 2 + 1), d_mel(a.n_mels > 0 ? a.n_mels : 1);  // index math without integer division (fft.cuh)
   const float* x = a.wave + (size_t)b * a.L;
   const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
 
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
   }
   __syncthreads();
   for (int i = threadIdx.x; i < G * M; i += blockDim.x) {
-    const int g = i / M, m = i - g * M;
+    const int g = d_M.div(i), m = i - g * M;
     float2 z = make_float2(0.f, 0.f);
     if (t0 + g < a.T) {
       const float* xf = xin + g * hop + 2 * m;  // scalar loads: hop may be odd
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
   // split into the one-sided spectrum
   const int half = M / 2 + 1;
   for (int i = threadIdx.x; i < G * half; i += blockDim.x) {
-    const int g = i / half, k = i - g * half;
+    const int g = d_half.div(i), k = i - g * half;
     const int t = t0 + g;
     if (t >= a.T) continue;
     const float2 zk = res[g * M + k];
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
   if (a.logmel_bt == nullptr && a.logmel_bm == nullptr) return;
   __syncthreads();
   for (int i = threadIdx.x; i < G * a.n_mels; i += blockDim.x) {
-    const int g = i / a.n_mels, m = i - g * a.n_mels;
+    const int g = d_mel.div(i), m = i - g * a.n_mels;
     const int t = t0 + g;
     if (t >= a.T) continue;
     const int lo = a.mel_lo[m], cnt = a.mel_cnt[m];

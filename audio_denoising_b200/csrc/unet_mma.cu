@@ -185,6 +185,30 @@ __device__ __forceinline__ void last_layer(const float* __restrict__ in, float* 
   }
 }
 
+// TMA bulk copy of the weight fragment image into shared memory (one instruction instead of a 16-round load / store loop:
+// it matters for the streaming hop, where a launch processes three frames and the prologue is most of the kernel)
+__device__ __forceinline__ uint32_t um_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void um_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(um_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(um_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(um_u32(dst)), "l"(src),
+               "r"(bytes), "r"(um_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void um_bulk_wait(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(um_u32(bar))
+      : "memory");
+}
+
 __device__ __forceinline__ void prefetch_range(const float* p, int bytes, int lane) {  // one 128-byte line per lane per round
   for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p) + o));
 }
@@ -200,14 +224,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decoder_mma_kernel(const float4
   float* PB = reinterpret_cast<float*>(FR + dfrag_off(4) * 32);        // position biases of the four layers
   float* act = PB + DPB_FLOATS;
   const Packed L = packed_layout();
-  for (int i = threadIdx.x; i < dfrag_off(4) * 32; i += blockDim.x) FR[i] = frags[i];
+  __shared__ uint64_t frag_bar;
+  if (threadIdx.x == 0) um_bulk_load(FR, frags, dfrag_off(4) * 32 * 16, &frag_bar);
   for (int l = 0; l < 4; ++l) {
     const int n = (l < 3 ? (8 << l) * HP : 64 * 4);
     for (int i = threadIdx.x; i < n; i += blockDim.x) PB[dpb_off(l) + i] = blob[L.dec_pb[l] + i];
   }
-  for (int i = threadIdx.x; i < WARPS * WARP_FLOATS; i += blockDim.x) act[i] = 0.f;  // padding channels / rows stay zero for good
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (((size_t)blockIdx.x * WARPS + warp) * G < nframes)  // only warps with work: padding channels / rows stay zero for good
+    for (int i = lane; i < WARP_FLOATS; i += 32) act[warp * WARP_FLOATS + i] = 0.f;
+  __syncthreads();
+  um_bulk_wait(&frag_bar);
   float* B0 = act + warp * WARP_FLOATS;  // layer inputs: rows fl * (Lin + 1) + i
   float* B1 = B0 + ROWS0 * S;
   float* B2 = B1 + ROWS1 * S;
@@ -383,14 +410,17 @@ __global__ void __launch_bounds__(EWARPS * 32, 1) encoder_mma_kernel(const float
   float* PB = reinterpret_cast<float*>(FR + efrag_off(4) * 32);
   float* act = PB + EPB_FLOATS;
   const Packed L = packed_layout();
-  for (int i = threadIdx.x; i < efrag_off(4) * 32; i += blockDim.x) FR[i] = frags[i];
+  __shared__ uint64_t frag_bar;
+  if (threadIdx.x == 0) um_bulk_load(FR, frags, efrag_off(4) * 32 * 16, &frag_bar);
   for (int l = 0; l < 4; ++l) {
     const int n = (l < 3 ? (32 >> l) * HP : 4 * H3P);
     for (int i = threadIdx.x; i < n; i += blockDim.x) PB[epb_off(l) + i] = blob[L.enc_pb[l] + i];
   }
-  for (int i = threadIdx.x; i < EWARPS * EWARP_FLOATS; i += blockDim.x) act[i] = 0.f;  // zero rows / unused channels stay zero
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (((size_t)blockIdx.x * EWARPS + warp) * G < nframes)  // only warps with work: zero rows / unused channels stay zero
+    for (int i = lane; i < EWARP_FLOATS + 8; i += 32) act[warp * EWARP_FLOATS + i] = 0.f;
+  __syncthreads();
+  um_bulk_wait(&frag_bar);
   float* X = act + warp * EWARP_FLOATS;
   float* A0 = X + G * EX;            // layer-1 input rows
   float* A1 = A0 + G * ER0 * ES;
@@ -507,7 +537,7 @@ int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* 
                      int num_sms, cudaStream_t st) {
   using namespace umma;
   B2D_REQUIRE(m->d_mma != nullptr, B2D_ERR_CUDA, "tensor-core weight fragments are missing");
-  const size_t smem = (size_t)efrag_off(4) * 32 * 16 + sizeof(float) * (EPB_FLOATS + (size_t)EWARPS * EWARP_FLOATS);
+  const size_t smem = (size_t)efrag_off(4) * 32 * 16 + sizeof(float) * (EPB_FLOATS + (size_t)EWARPS * EWARP_FLOATS) + 64;  // + slack behind the last warp
   const size_t want = (nframes + EWARPS * G - 1) / (EWARPS * G);
   const int grid = (int)(want < (size_t)num_sms ? want : (size_t)num_sms);
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma) + (size_t)dfrag_off(4) * 32;
