@@ -108,8 +108,6 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
     f_store_prev = (it + 1 < a.fused_iters && a.mom != 0.f);
     cur_in = (step & 1) ? a.xa : a.xb;   // step 0 writes xa, step 1 reads xa writes xb, ...
     cur_out = (step & 1) ? a.xb : a.xa;
-    for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = 0.f;
-    __syncthreads();
   }
   float* xo = cur_out + (size_t)(b * R + r) * (n + 1) * hop;
 
@@ -220,12 +218,15 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       const int c = d_hop.div(idx), i = idx - c * hop;
       const float prev = (c == 0) ? carry_s[i] : y[(c - 1) * N + hop + i] * a.winn[hop + i];
       xo[(size_t)(tb - tbeg + c) * hop + i] = prev + y[c * N + i] * a.winn[i];
+      // the thread that consumed carry_s[i] (c == 0, idx == i) is the one that replaces it: no barrier in between
+      if (c == 0) carry_s[i] = y[(gv - 1) * N + hop + i] * a.winn[hop + i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < hop; i += blockDim.x) carry_s[i] = y[(gv - 1) * N + hop + i] * a.winn[hop + i];
-    __syncthreads();
   }
-  for (int i = threadIdx.x; i < hop; i += blockDim.x) xo[(size_t)(tend - tbeg) * hop + i] = carry_s[i];
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+    xo[(size_t)(tend - tbeg) * hop + i] = carry_s[i];
+    carry_s[i] = 0.f;  // ready for the next fused step
+  }
   __syncthreads();  // fused mode: this CTA's global writes are visible to all its threads before the next step reads them
   }  // step
 }
