@@ -20,7 +20,7 @@ m = adb.GRUUNet2(**cfg); m.load_state_dict(sd); m = m.to(dev).eval()
 m.conv_mode = os.environ.get('CONV_MODE', m.conv_mode)
 rows = []
 for sr, n_fft, hop in [(16000, 640, 320), (48000, 1536, 768), (16000, 1024, 512)]:
-    for S in (1, 64):
+    for S in [int(v) for v in os.environ.get('STREAM_SESSIONS', '1,64').split(',')]:
         sdn = adb.StreamingDenoiser(m, n_fft=n_fft, hop_length=hop, n_mels=64, sample_rate=sr, sessions=S)
         rng = np.random.default_rng(0)
         sig = (rng.standard_normal((S, n_fft + hop * (hops + warm))) * 0.1).astype(np.float32)
