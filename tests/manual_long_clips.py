@@ -1,0 +1,24 @@
+"""Run by hand (python tests/manual_long_clips.py): the three register Griffin-Lim paths against the generic kernel on
+very long clips (T up to 18751) and on thousands of 4-frame clips; prints SI-SDR, no asserts."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from audio_denoising_b200 import _cabi, _runtime
+from oracle import metrics
+dev = torch.device("cuda:0"); lib = _cabi.lib(); st = torch.cuda.current_stream().cuda_stream
+g = torch.Generator().manual_seed(1)
+for n_fft in (512, 1024, 2048):
+    plan = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev)
+    for B, T in [(2, 3126), (1, 18751), (3000, 4)]:
+        mag = (torch.rand(B, T, plan.frame_stride, generator=g) * 2).to(dev)
+        ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(plan.handle, B, T), dtype=torch.uint8, device=dev)
+        outs = []
+        for generic in (False, True):
+            if generic: os.environ["B2D_GL_GENERIC"] = "1"
+            else: os.environ.pop("B2D_GL_GENERIC", None)
+            wave = torch.zeros(B, plan.out_length(T), device=dev)
+            _cabi.check(lib.b2d_griffinlim_frames(plan.handle, mag.data_ptr(), None, 0, B, T, 2, 0.99, None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            torch.cuda.synchronize(); outs.append(wave.cpu())
+        os.environ.pop("B2D_GL_GENERIC", None)
+        s = metrics.si_sdr(outs[0], outs[1])
+        print(n_fft, B, T, "median", round(float(s.median()), 1), "min", round(float(s.min()), 1), flush=True)
