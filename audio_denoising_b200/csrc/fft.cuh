@@ -221,6 +221,35 @@ __device__ __forceinline__ float2* fft_rows(float2* a, float2* b, int rows, int 
   return a;
 }
 
+// The same with the length (and hence the radix sequence of api.cu's factor(): 8s, 4s, 2s, 3s, 5s) known at compile time,
+// for the two streaming geometries (n_fft 640 -> M = 320 = 8 8 5, n_fft 1536 -> M = 768 = 8 8 4 3): every index
+// computation folds to constants.  MT == 0 falls back to the run-time description.
+template <bool INV, int MT>
+__device__ __forceinline__ float2* fft_rows_t(float2* a, float2* b, int rows, int ld, const FftDesc& fd,
+                                              const float2* __restrict__ tw) {
+  if (MT == 320) {
+    stockham_pass<INV, 8>(a, b, rows, 320, ld, 1, tw);
+    __syncthreads();
+    stockham_pass<INV, 8>(b, a, rows, 320, ld, 8, tw);
+    __syncthreads();
+    stockham_pass<INV, 5>(a, b, rows, 320, ld, 64, tw);
+    __syncthreads();
+    return b;
+  }
+  if (MT == 768) {
+    stockham_pass<INV, 8>(a, b, rows, 768, ld, 1, tw);
+    __syncthreads();
+    stockham_pass<INV, 8>(b, a, rows, 768, ld, 8, tw);
+    __syncthreads();
+    stockham_pass<INV, 4>(a, b, rows, 768, ld, 64, tw);
+    __syncthreads();
+    stockham_pass<INV, 3>(b, a, rows, 768, ld, 256, tw);
+    __syncthreads();
+    return a;
+  }
+  return fft_rows<INV>(a, b, rows, ld, fd, tw);
+}
+
 // Real-FFT split: Z = FFT_M(x[2m] + i x[2m+1]) -> X[k], X[M-k] for one pair index k in [0, M/2].
 // rt = W_N^k.  (k == 0 yields X[0] and X[M], both real; k == M/2 yields the same bin twice.)
 B2D_HD void rfft_split(float2 zk, float2 zmk, float2 rt, float2& xk, float2& xmk) {

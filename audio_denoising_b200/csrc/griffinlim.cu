@@ -76,9 +76,11 @@ __device__ __forceinline__ float2 unit_dir(float2 a) {
   return make_float2(a.x * inv, a.y * inv);
 }
 
+// MT: complex transform length known at compile time (320 / 768: the streaming geometries n_fft 640 / 1536, hop = M) or 0
+template <int MT>
 __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int M = a.M, N = a.n_fft, G = a.G, hop = a.hop, n = a.n, R = a.R, T = a.T;
+  const int M = MT ? MT : a.M, N = MT ? 2 * MT : a.n_fft, G = a.G, hop = MT ? MT : a.hop, n = a.n, R = a.R, T = a.T;
   float2* tw_s = reinterpret_cast<float2*>(smem_raw);
   float2* bufA = tw_s + M;
   float2* bufB = bufA + G * M;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
         bufA[idx] = z;
       }
       __syncthreads();
-      float2* res = fft_rows<false>(bufA, bufB, G, M, a.fd, tw_s);
+      float2* res = fft_rows_t<false, MT>(bufA, bufB, G, M, a.fd, tw_s);
       for (int idx = threadIdx.x; idx < gv * half; idx += blockDim.x) {
         const int g = d_half.div(idx), k = idx - g * half;
         const int t = tb + g;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       src = bufA;
       other = bufB;
     }
-    float2* out = fft_rows<true>(src, other, G, M, a.fd, tw_s);
+    float2* out = fft_rows_t<true, MT>(src, other, G, M, a.fd, tw_s);
     const float* y = reinterpret_cast<const float*>(out);
     for (int idx = threadIdx.x; idx < gv * hop; idx += blockDim.x) {
       const int c = d_hop.div(idx), i = idx - c * hop;
@@ -367,7 +369,15 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = momentum / (1.0f + momentum);
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * q.G * p->M) + sizeof(float) * (size_t)((q.G + 2) * p->hop) + 16;
-  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int mt = (p->hop == p->M && p->M == 320) ? 320 : (p->hop == p->M && p->M == 768) ? 768 : 0;
+  auto launch_generic = [&](dim3 g, const GlArgs& args) {
+    if (mt == 320) gl_generic_kernel<320><<<g, 256, smem, st>>>(args);
+    else if (mt == 768) gl_generic_kernel<768><<<g, 256, smem, st>>>(args);
+    else gl_generic_kernel<0><<<g, 256, smem, st>>>(args);
+  };
   dim3 grid(q.R, B);
   a.fused_iters = -1; a.xa = xa; a.xb = xb;
   float* cur = xa;
@@ -377,7 +387,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     // short clips (streaming hops: T = 3): every dependency stays inside one CTA -> init + all iterations in one launch
     a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
     a.fused_iters = n_iter;
-    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+    launch_generic(grid, a);
     B2D_LAUNCH_CHECK("gl_generic_kernel(fused)");
     cur = (n_iter & 1) ? xb : xa;  // step s writes xa when s is even; the last step is s = n_iter
   } else {
@@ -390,7 +400,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     int rc = launch_gl_fast_n2048_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
     if (rc != B2D_OK) return rc;
   } else {
-    gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+    launch_generic(grid, a);
     B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
   }
   a.init = 0; a.angles0 = nullptr;
@@ -414,7 +424,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
       if (rc != B2D_OK) return rc;
       direct_interior = last;
     } else {
-      gl_generic_kernel<<<grid, 256, smem, st>>>(a);
+      launch_generic(grid, a);
       B2D_LAUNCH_CHECK("gl_generic_kernel");
     }
     float* t = cur; cur = nxt; nxt = t;
