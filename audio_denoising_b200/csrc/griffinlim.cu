@@ -126,7 +126,16 @@ __global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
       for (int idx = threadIdx.x; idx < (gv + 1 - first) * hop; idx += blockDim.x) {
         const int cq = d_hop.div(idx);
         const int c = first + cq, i = idx - cq * hop;
-        xin_s[c * hop + i] = x_padded(cur_in, a.inv_env, b, R, d_n, hop, T, tb + c, i);
+        if (a.fused_iters >= 0) {
+          // fused mode: the run is the whole clip (R == 1, n >= T), so no hop-block is split over two runs
+          const int j = tb + c;
+          int js = j, is = i;
+          if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : hop - i; }
+          else if (j == T) { js = (i == hop - 1) ? T - 2 : T - 1; is = (i == hop - 1) ? hop - 1 : hop - 2 - i; }
+          xin_s[c * hop + i] = cur_in[((size_t)b * (n + 1) + js) * hop + is] * a.inv_env[is];
+        } else {
+          xin_s[c * hop + i] = x_padded(cur_in, a.inv_env, b, R, d_n, hop, T, tb + c, i);
+        }
       }
       __syncthreads();
       for (int idx = threadIdx.x; idx < G * M; idx += blockDim.x) {
