@@ -78,7 +78,7 @@ __device__ __forceinline__ float2 unit_dir(float2 a) {
 
 // MT: complex transform length known at compile time (320 / 768: the streaming geometries n_fft 640 / 1536, hop = M) or 0
 template <int MT>
-__global__ void __launch_bounds__(256) gl_generic_kernel(const GlArgs a) {
+__global__ void __launch_bounds__(1024) gl_generic_kernel(const GlArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = MT ? MT : a.M, N = MT ? 2 * MT : a.n_fft, G = a.G, hop = MT ? MT : a.hop, n = a.n, R = a.R, T = a.T;
   float2* tw_s = reinterpret_cast<float2*>(smem_raw);
@@ -383,9 +383,18 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int mt = (p->hop == p->M && p->M == 320) ? 320 : (p->hop == p->M && p->M == 768) ? 768 : 0;
   auto launch_generic = [&](dim3 g, const GlArgs& args) {
-    if (mt == 320) gl_generic_kernel<320><<<g, 256, smem, st>>>(args);
-    else if (mt == 768) gl_generic_kernel<768><<<g, 256, smem, st>>>(args);
-    else gl_generic_kernel<0><<<g, 256, smem, st>>>(args);
+    int threads = 256;
+    if (args.fused_iters >= 0) {
+      // one CTA walks all the steps of a short clip alone: give it the whole SM (measured per-hop latency, n_fft 640 /
+      // 1536: 0.222 / 0.579 ms with 256 threads, 0.207 / 0.371 with 512, 0.211 / 0.357 with 1024)
+      threads = p->M >= 640 ? 1024 : (p->M >= 256 ? 512 : 256);
+      const char* ft = getenv("B2D_GL_FUSED_THREADS");
+      if (ft) threads = atoi(ft);
+      if (threads < 32 || threads > 1024 || (threads & 31)) threads = 256;
+    }
+    if (mt == 320) gl_generic_kernel<320><<<g, threads, smem, st>>>(args);
+    else if (mt == 768) gl_generic_kernel<768><<<g, threads, smem, st>>>(args);
+    else gl_generic_kernel<0><<<g, threads, smem, st>>>(args);
   };
   dim3 grid(q.R, B);
   a.fused_iters = -1; a.xa = xa; a.xb = xb;
