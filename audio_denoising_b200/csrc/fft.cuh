@@ -236,6 +236,15 @@ __device__ __forceinline__ float2* fft_rows_t(float2* a, float2* b, int rows, in
     __syncthreads();
     return b;
   }
+  if (MT == 512) {
+    stockham_pass<INV, 8>(a, b, rows, 512, ld, 1, tw);
+    __syncthreads();
+    stockham_pass<INV, 8>(b, a, rows, 512, ld, 8, tw);
+    __syncthreads();
+    stockham_pass<INV, 8>(a, b, rows, 512, ld, 64, tw);
+    __syncthreads();
+    return b;
+  }
   if (MT == 768) {
     stockham_pass<INV, 8>(a, b, rows, 768, ld, 1, tw);
     __syncthreads();
