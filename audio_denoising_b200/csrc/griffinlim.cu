@@ -71,8 +71,15 @@ __device__ __forceinline__ float x_padded(const float* part, const float* __rest
   return x_block_sample(part, inv_env, b, R, dn, hop, j, i);
 }
 
+// a / (|a| + 1e-16) through the reciprocal-square-root unit (one MUFU instead of an IEEE square root and division): for
+// |a| >= 1e-15 the epsilon is below fp32 resolution, for |a| -> 0 both forms tend to a * 1e16 and give 0 for a == 0
+__device__ __forceinline__ float inv_abs(float s) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 1e-32f)));
+  return r;
+}
 __device__ __forceinline__ float2 unit_dir(float2 a) {
-  const float inv = 1.0f / (sqrtf(a.x * a.x + a.y * a.y) + 1e-16f);
+  const float inv = inv_abs(a.x * a.x + a.y * a.y);
   return make_float2(a.x * inv, a.y * inv);
 }
 
@@ -168,8 +175,8 @@ __global__ void __launch_bounds__(1024) gl_generic_kernel(const GlArgs a) {
             a0 -= a.mom * pv.x;
             aM -= a.mom * pv.y;
           }
-          yk = make_float2(mk * (a0 / (fabsf(a0) + 1e-16f)), 0.f);
-          ymk = make_float2(mmk * (aM / (fabsf(aM) + 1e-16f)), 0.f);
+          yk = make_float2(mk * (a0 * inv_abs(a0 * a0)), 0.f);
+          ymk = make_float2(mmk * (aM * inv_abs(aM * aM)), 0.f);
           if (f_store_prev) tp[0] = make_float2(xk.x, xmk.x);
         } else {
           float2 ak = xk, amk = xmk;
