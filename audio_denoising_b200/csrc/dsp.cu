@@ -74,9 +74,11 @@ struct StftArgs {
   float* logmel_bm;  // [B,n_mels,T] or null
 };
 
-__global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
+// MT: complex transform length known at compile time (fft_rows_t: 320 / 512 / 768) or 0
+template <int MT>
+__global__ void __launch_bounds__(512) stft_kernel(const StftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int M = a.M, N = a.n_fft, G = a.G, hop = a.hop;
+  const int M = MT ? MT : a.M, N = MT ? 2 * MT : a.n_fft, G = a.G, hop = a.hop;
   float2* tw_s = reinterpret_cast<float2*>(smem_raw);
   float2* bufA = tw_s + M;
   float2* bufB = bufA + G * M;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const StftArgs a) {
     bufA[i] = z;
   }
   __syncthreads();
-  float2* res = fft_rows<false>(bufA, bufB, G, M, a.fd, tw_s);
+  float2* res = fft_rows_t<false, MT>(bufA, bufB, G, M, a.fd, tw_s);
   // split into the one-sided spectrum
   const int half = M / 2 + 1;
   for (int i = threadIdx.x; i < G * half; i += blockDim.x) {
@@ -387,9 +389,22 @@ int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, in
   a.spec = spec; a.logmel_bt = logmel_bt; a.logmel_bm = logmel_bm;
   const int xlen = (a.G - 1) * p->hop + p->n_fft;
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * a.G * p->M) + sizeof(float) * (size_t)(xlen + a.G * (p->M + 1)) + 16;
-  B2D_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((a.T + a.G - 1) / a.G, B);
-  stft_kernel<<<grid, 256, smem, st>>>(a);
+  // a streaming hop is a single CTA per session: give it more threads; batches keep 256 (several CTAs per SM)
+  const int threads = ((long)grid.x * grid.y <= 2 * p->num_sms) ? 512 : 256;
+  if (p->M == 320) {
+    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<320><<<grid, threads, smem, st>>>(a);
+  } else if (p->M == 512) {
+    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<512><<<grid, threads, smem, st>>>(a);
+  } else if (p->M == 768) {
+    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<768><<<grid, threads, smem, st>>>(a);
+  } else {
+    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<0><<<grid, threads, smem, st>>>(a);
+  }
   B2D_LAUNCH_CHECK("stft_kernel");
   return B2D_OK;
 }
