@@ -402,7 +402,11 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int mt = (p->hop != p->M) ? 0 : (p->M == 320 || p->M == 512 || p->M == 768) ? p->M : 0;
   auto launch_generic = [&](dim3 g, const GlArgs& args) {
-    int threads = 256;
+    int threads = p->M >= 640 ? 512 : 256;  // batch mode, measured at B = 256: n_fft 1536 1259 -> 1128 us per iteration with 512
+    if (const char* gt = getenv("B2D_GL_GENERIC_THREADS")) {
+      threads = atoi(gt);
+      if (threads < 32 || threads > 1024 || (threads & 31)) threads = 256;
+    }
     if (args.fused_iters >= 0) {
       // one CTA walks all the steps of a short clip alone: give it the whole SM (measured per-hop latency, n_fft 640 /
       // 1536: 0.222 / 0.579 ms with 256 threads, 0.207 / 0.371 with 512, 0.211 / 0.357 with 1024)
