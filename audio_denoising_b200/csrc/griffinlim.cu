@@ -275,6 +275,10 @@ int launch_gl_fast_n2048(const b2d_plan* p, const float* mag_tf, float2* tprev, 
 int gl_fast_n2048_warps();
 int launch_gl_fast_n2048_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                               const unsigned long long* seed_ptr, cudaStream_t st);
+int launch_gl_warp(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n, int R,
+                   float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_warp.cu
+int gl_warp_warps(const b2d_plan* p);
+bool gl_warp_supported(const b2d_plan* p);
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            const unsigned long long* seed_ptr, cudaStream_t st);
 
@@ -306,11 +310,13 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
     if (p->n_fft == 1024 && p->hop == 512) q.fast = 1;
     if (p->n_fft == 512 && p->hop == 256) q.fast = 2;
     if (p->n_fft == 2048 && p->hop == 1024) q.fast = 3;
+    // every other length with hop = n_fft / 2 (640, 1536 ...): warp-synchronous Stockham kernel (gl_warp.cu)
+    if (!q.fast && gl_warp_supported(p) && getenv("B2D_GL_NO_WARP") == nullptr) q.fast = 4;
   }
   if (q.fast) {
     // one warp per run.  Pick the number of runs per clip R that minimises the busiest SM's load
     // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
-    const int wps = q.fast == 3 ? gl_fast_n2048_warps() : gl_fast_warps_per_sm();
+    const int wps = q.fast == 3 ? gl_fast_n2048_warps() : q.fast == 4 ? gl_warp_warps(p) : gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
     const char* mn = getenv("B2D_GL_MIN_RUN");
     const int min_run = mn ? (atoi(mn) < 1 ? 1 : atoi(mn)) : 2;  // frames per run: short runs cut the latency of small batches
@@ -458,6 +464,9 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
       direct_interior = last;
     } else if (q.fast == 2) {
       int rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
+      if (rc != B2D_OK) return rc;
+    } else if (q.fast == 4) {
+      int rc = launch_gl_warp(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
       if (rc != B2D_OK) return rc;
     } else if (q.fast == 3) {
       const bool last = (it + 1 == n_iter) && getenv("B2D_GL_NO_DIRECT") == nullptr;

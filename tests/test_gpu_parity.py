@@ -675,7 +675,7 @@ def test_denoise_host_pcm16_matches_float_path(dev):
         pipe.denoise_host(torch.zeros(2, 16000, dtype=torch.float64).pin_memory())
 
 
-@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048, 640, 1536])
 def test_fast_paths_match_generic_on_ragged_shapes(dev, monkeypatch, n_fft):
     """Run partitions of every flavour (single short run, odd run lengths, a last run of one frame, more runs than warp
     slots) for the three register fast paths: 3 iterations from all-ones angles against the generic kernel."""
