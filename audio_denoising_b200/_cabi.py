@@ -64,6 +64,8 @@ SIGNATURES = {
     "b2d_istft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b2d_denoise_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
     "b2d_denoise_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _u64, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2d_denoise_pcm16_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
+    "b2d_denoise_batch_pcm16": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _u64, _i, _f, _i, _i, _vp, _vp, _sz, _vp]),
     "b2d_denoise_noisy_phase_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
     "b2d_denoise_noisy_phase": (_i, [_vp, _vp, _vp, _i, _i, _vp, _f, _f, _i, _vp, _vp, _sz, _vp]),
     "b2d_stream_step_workspace_bytes": (_sz, [_vp, _vp, _i]),

@@ -115,15 +115,20 @@ def get_plan(n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.
 
 
 class Workspace:
-    """Grow-only byte buffer on one device (caller-owned scratch for the native calls)."""
+    """Grow-only byte buffers (caller-owned scratch for the native calls), one per (device, CUDA stream): work enqueued on
+    different streams may overlap on the GPU, so it must not share scratch memory."""
 
     def __init__(self):
-        self._buf: torch.Tensor | None = None
+        self._bufs: dict = {}
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
-        if self._buf is None or self._buf.device != device or self._buf.numel() < nbytes:
-            self._buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        return self._buf
+        device = torch.device(device)
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
 
 
 def draw_seed() -> int:

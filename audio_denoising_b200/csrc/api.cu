@@ -358,6 +358,28 @@ size_t b2d_denoise_workspace_bytes(const b2d_plan* plan, const b2d_model* model,
   return chain_layout(plan, model, B, T, nullptr, true, false).total;
 }
 
+// peak (unless the ingest kernel already produced it) -> STFT+Mel -> GRUUNet2 (+residual) -> inverse mel -> Griffin-Lim
+static int denoise_chain(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L, int T, float* hx,
+                         const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int normalise,
+                         bool peak_ready, int conv_mode, float* wave, float* logmel_bt, float* pred_bt, float* mag_tf,
+                         const ChainWs& w, cudaStream_t st) {
+  int rc;
+  float* logmel = logmel_bt ? logmel_bt : w.logmel;
+  float* pred = pred_bt ? pred_bt : w.pred;
+  float* mag = mag_tf ? mag_tf : w.mag;
+  if (normalise && !peak_ready && (rc = launch_peak(noisy, B, L, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
+  if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
+  if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
+  // inverse mel: tcgen05 GEMM (TF32 big/small split = fp32-class) when the plan has the weight images, else the CUDA-core SGEMM
+  if (plan->d_tw8 != nullptr) {
+    if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, 3, st))) return rc;
+  } else if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) {
+    return rc;
+  }
+  return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum,
+                normalise ? w.peak : nullptr, wave, w.gl_ws, w.gl_bytes, st);
+}
+
 int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float* noisy, int B, int L, float* hx,
                       const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int normalise,
                       int conv_mode, float* wave,
@@ -371,22 +393,47 @@ int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float*
   B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "clip too short: need at least 3 frames");
   const ChainWs w = chain_layout(plan, model, B, T, workspace, true, false);
   B2D_REQUIRE(workspace_bytes >= w.total, B2D_ERR_WORKSPACE, "denoise workspace too small (%zu < %zu)", workspace_bytes, w.total);
+  return denoise_chain(plan, model, noisy, B, L, T, hx, init_angles, seed, n_iter, momentum, normalise, false, conv_mode, wave,
+                       logmel_bt, pred_bt, mag_tf, w, ST(stream));
+}
+
+// ---- the same chain on the int16 PCM link (app3.py:168-172 in, :244-245 out) ----------------------
+// workspace: float noisy[B, L] | float wave[B, Lout] | chain workspace
+size_t b2d_denoise_pcm16_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L) {
+  const size_t chain = b2d_denoise_workspace_bytes(plan, model, B, L);
+  if (!chain) return 0;
+  const int T = 1 + L / plan->hop;
+  return align_up((size_t)B * L * sizeof(float), 256) + align_up((size_t)B * plan->hop * (T - 1) * sizeof(float), 256) + chain;
+}
+
+int b2d_denoise_batch_pcm16(const b2d_plan* plan, const b2d_model* model, const short* pcm, int B, int L, float* hx,
+                            const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum, int normalise,
+                            int conv_mode, short* pcm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  B2D_REQUIRE(plan && pcm, B2D_ERR_BAD_ARG, "NULL pointer");
+  CHECK_BATCH(B);
+  B2D_REQUIRE(L > plan->n_fft / 2, B2D_ERR_BAD_ARG,
+              "reflect padding needs L > n_fft/2 (L=%d, n_fft=%d) -- same restriction as torch.stft", L, plan->n_fft);
+  B2D_REQUIRE(model && hx && pcm_out && workspace, B2D_ERR_BAD_ARG, "NULL pointer");
+  B2D_REQUIRE(model->n_mels == plan->n_mels, B2D_ERR_BAD_ARG, "plan n_mels (%d) != model n_mels (%d)", plan->n_mels, model->n_mels);
+  B2D_REQUIRE(aligned16(workspace), B2D_ERR_ALIGN, "workspace must be 16-byte aligned");
+  const int T = 1 + L / plan->hop;
+  B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "clip too short: need at least 3 frames");
+  const size_t need = b2d_denoise_pcm16_workspace_bytes(plan, model, B, L);
+  B2D_REQUIRE(workspace_bytes >= need, B2D_ERR_WORKSPACE, "denoise workspace too small (%zu < %zu)", workspace_bytes, need);
+  unsigned char* base = static_cast<unsigned char*>(workspace);
+  float* noisy = reinterpret_cast<float*>(base);
+  const size_t nb = align_up((size_t)B * L * sizeof(float), 256);
+  float* wave = reinterpret_cast<float*>(base + nb);
+  const size_t nout = (size_t)B * plan->hop * (T - 1);
+  const size_t wb = align_up(nout * sizeof(float), 256);
+  const ChainWs w = chain_layout(plan, model, B, T, base + nb + wb, true, false);
   cudaStream_t st = ST(stream);
-  float* logmel = logmel_bt ? logmel_bt : w.logmel;
-  float* pred = pred_bt ? pred_bt : w.pred;
-  float* mag = mag_tf ? mag_tf : w.mag;
-  if (normalise && (rc = launch_peak(noisy, B, L, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
-  if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
-  if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
-  // inverse mel: tcgen05 GEMM (TF32 big/small split = fp32-class; single pass only in conv_mode 2) when the plan has the
-  // weight images, else the CUDA-core SGEMM
-  if (plan->d_tw8 != nullptr && getenv("B2D_INVMEL_FP32") == nullptr) {
-    if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, conv_mode == 2 ? 1 : 3, st))) return rc;
-  } else if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) {
+  int rc;
+  if ((rc = launch_pcm16_ingest_peak(pcm, B, L, noisy, w.peak, w.peak + B, L >= 16384 ? kPeakChunks : 1, st))) return rc;
+  if ((rc = denoise_chain(plan, model, noisy, B, L, T, hx, init_angles, seed, n_iter, momentum, normalise, true, conv_mode, wave,
+                          nullptr, nullptr, nullptr, w, st)))
     return rc;
-  }
-  return gl_run(plan, mag, reinterpret_cast<const float2*>(init_angles), seed, B, T, n_iter, momentum,
-                normalise ? w.peak : nullptr, wave, w.gl_ws, w.gl_bytes, st);
+  return b2d_float_to_pcm16(wave, nout, pcm_out, stream);
 }
 
 size_t b2d_denoise_noisy_phase_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L) {

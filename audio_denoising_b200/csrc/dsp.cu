@@ -44,6 +44,56 @@ __global__ void __launch_bounds__(256) peak_partial_kernel(const float* __restri
     if (threadIdx.x == 0) partial[b * chunks + blockIdx.x] = m;
   }
 }
+// int16 PCM rows -> float (x / 32767, app3.py:172) with the peak partials of K0 taken in the same pass (the float copy is
+// written once and never re-read for the peak): the ingest of the int16 host link (b2d_denoise_batch_pcm16)
+__global__ void __launch_bounds__(256) pcm16_ingest_peak_kernel(const short* __restrict__ pcm, int L, int chunks,
+                                                                float* __restrict__ wave, float* __restrict__ partial) {
+  const int b = blockIdx.y;
+  const short* x = pcm + (size_t)b * L;
+  float* y = wave + (size_t)b * L;
+  const int per = ((L + chunks - 1) / chunks + 7) & ~7;
+  const int lo = min(L, (int)blockIdx.x * per), hi = min(L, lo + per);
+  float m = 0.f;
+  if (((((size_t)x) & 15) | (((size_t)y) & 15)) == 0) {  // 8 samples per thread: one 16-byte load, two 16-byte stores
+    const int4* x8 = reinterpret_cast<const int4*>(x + lo);
+    float4* y4 = reinterpret_cast<float4*>(y + lo);
+    const int n8 = (hi - lo) >> 3;
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+      const int4 q = x8[i];
+      const int w[4] = {q.x, q.y, q.z, q.w};
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[2 * e] = (float)(short)(w[e] & 0xffff) / 32767.0f;
+        v[2 * e + 1] = (float)(short)(w[e] >> 16) / 32767.0f;
+      }
+      y4[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+      y4[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(v[e]));
+    }
+    for (int j = lo + 8 * n8 + threadIdx.x; j < hi; j += blockDim.x) {
+      const float v = (float)x[j] / 32767.0f;
+      y[j] = v;
+      m = fmaxf(m, fabsf(v));
+    }
+  } else {
+    for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+      const float v = (float)x[j] / 32767.0f;
+      y[j] = v;
+      m = fmaxf(m, fabsf(v));
+    }
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = s[threadIdx.x];
+    for (int o = 4; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) partial[b * chunks + blockIdx.x] = m;
+  }
+}
 __global__ void peak_final_kernel(const float* __restrict__ partial, int B, int chunks, float* __restrict__ peak) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -368,6 +418,14 @@ static int frames_per_block(const b2d_plan* p) { return p->M <= 1024 ? 4 : 2; }
 int launch_peak(const float* wave, int B, int L, float* peak, float* partial, int chunks, cudaStream_t st) {
   peak_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(wave, L, chunks, partial);
   B2D_LAUNCH_CHECK("peak_partial_kernel");
+  peak_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(partial, B, chunks, peak);
+  B2D_LAUNCH_CHECK("peak_final_kernel");
+  return B2D_OK;
+}
+
+int launch_pcm16_ingest_peak(const short* pcm, int B, int L, float* wave, float* peak, float* partial, int chunks, cudaStream_t st) {
+  pcm16_ingest_peak_kernel<<<dim3(chunks, B), 256, 0, st>>>(pcm, L, chunks, wave, partial);
+  B2D_LAUNCH_CHECK("pcm16_ingest_peak_kernel");
   peak_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(partial, B, chunks, peak);
   B2D_LAUNCH_CHECK("peak_final_kernel");
   return B2D_OK;

@@ -7,6 +7,8 @@ namespace b2d {
 
 // dsp.cu
 int launch_peak(const float* wave, int B, int L, float* peak, float* partial, int chunks, cudaStream_t st);
+// int16 PCM [B, L] -> float wave [B, L] (x / 32767) + peak[B] (same rule as launch_peak) in one pass
+int launch_pcm16_ingest_peak(const short* pcm, int B, int L, float* wave, float* peak, float* partial, int chunks, cudaStream_t st);
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                 float* logmel_bm, float2* spec, cudaStream_t st);
 int launch_mel_scale(const b2d_plan* p, const float* mag, int B, int T, float* mel, cudaStream_t st);

@@ -15,6 +15,7 @@ CUDA float32 tensors only; no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 from typing import Optional, Sequence
 
@@ -22,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from ._runtime import Workspace, require_cuda_f32, stream_ptr
+from ._runtime import require_cuda_f32, stream_ptr
 
 # "fp32": CUDA-core FMA convolutions; "tf32x3": tcgen05 implicit GEMM, operands split into big+small TF32 parts (3 MMAs,
 # fp32-class accuracy); "tf32": tcgen05 single pass (11-bit mantissa operands, fp32 accumulate); "mma": warp-level m16n8k8
@@ -76,6 +77,15 @@ class _Cell(nn.Module):  # "input_gate", "reset_gate", "output_gate"
         self.output_gate = _Decoder(hs[::-1] + [1], list(kernel_sizes)[::-1], list(strides)[::-1], list(paddings)[::-1], count)
 
 
+class NativeModel:
+    """One packed ``b2d_model`` (weights re-laid-out on one device).  Immutable; destroyed when the last Python reference
+    goes away, so a CUDA graph or pipeline that captured its device pointers keeps it alive by holding this object."""
+
+    def __init__(self, handle, signature, device_index: int):
+        self.handle, self.signature, self.device_index = handle, signature, device_index
+        self._fin = weakref.finalize(self, _cabi.lib().b2d_model_destroy, handle)
+
+
 class GRUUNet2(nn.Module):
     def __init__(self, num_compressed_bins, in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians=6):
         super().__init__()
@@ -87,9 +97,10 @@ class GRUUNet2(nn.Module):
         self.latent_size = hidden_sizes[-1]
         self.num_compressed_bins = num_compressed_bins
         self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
-        self.conv_mode = "mma"  # one of CONV_MODES (default: tensor-core MMAs with the fp32-class big+small TF32 split)
-        self._native = None  # (signature, handle, finalizer)
-        self._ws = Workspace()
+        self.conv_mode = "mma"  # one of CONV_MODES
+        self._native = {}  # device index -> NativeModel
+        self._native_lock = threading.Lock()
+        self._generation = 0  # bumped by repack()
 
     # ---- gruunet2.py:29-51 helpers ------------------------------------------------------------
     def get_config(self):
@@ -101,41 +112,58 @@ class GRUUNet2(nn.Module):
 
     @property
     def n_mels(self) -> int:
-        return self.num_compressed_bins << len(self.hparams["hidden_sizes"])
+        """Length of the model's input axis: the conv length formula of gruunet2.py:127-157 run backwards from
+        ``num_compressed_bins`` (L_in = (L_out - 1) * s - 2 p + k; ``bins << levels`` for the shipped k3 s2 p1)."""
+        hp = self.hparams
+        n = self.num_compressed_bins
+        for k, s, p in zip(reversed(list(hp["kernel_sizes"])), reversed(list(hp["strides"])), reversed(list(hp["paddings"]))):
+            n = (n - 1) * s - 2 * p + k + (s - 1 if s > 1 else 0)  # + s - 1: the largest length that still maps to n (64 -> 32)
+        return n
 
     # ---- native model management -------------------------------------------------------------
     def _signature(self):
         ps = list(self.parameters()) + list(self.buffers())
-        return tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+        return (self._generation,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+
+    def repack(self) -> None:
+        """Force a re-pack on next use.  Needed only after edits autograd cannot see (``p.data.mul_()``, writes through a
+        numpy view): ``load_state_dict``, ``optimizer.step`` and ``.to()`` bump the version counters and are picked up
+        automatically."""
+        with self._native_lock:
+            self._generation += 1
+
+    def native_model(self, device: torch.device) -> NativeModel:
+        """The packed native model for ``device`` (re-packed after any weight change).  Handles are cached per device
+        and never destroyed while something still references them: callers that bake device pointers into a CUDA
+        graph keep the returned object (``StreamingDenoiser`` does) and compare identities to notice a re-pack."""
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._native_lock:
+            sig = self._signature()
+            cur = self._native.get(idx)
+            if cur is not None and cur.signature == sig:
+                return cur
+            hp = self.hparams
+            hs = list(hp["hidden_sizes"])
+            uniform = all(h == hs[0] for h in hs)
+            ks, ss, pp = set(hp["kernel_sizes"]), set(hp["strides"]), set(hp["paddings"])
+            if not (uniform and len(ks) == 1 and len(ss) == 1 and len(pp) == 1):
+                raise NotImplementedError(f"GRUUNet2 (B200): non-uniform layer config is not implemented: {hp}")
+            cfg = _cabi.ModelConfig(hp["num_compressed_bins"], hs[0], len(hs), ks.pop(), ss.pop(), pp.pop(), hp["num_gaussians"])
+            params = [p.detach().to("cpu", torch.float32).contiguous() for p in self.parameters()]
+            offs = [g.gs.offset.detach().to("cpu", torch.float32).contiguous()
+                    for g in (self.cell.input_gate, self.cell.reset_gate, self.cell.output_gate)]
+            parr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            oarr = (C.c_void_p * 3)(*[o.data_ptr() for o in offs])
+            handle = C.c_void_p()
+            with torch.cuda.device(idx):
+                _cabi.check(_cabi.lib().b2d_model_create(C.byref(cfg), parr, len(params), oarr, C.byref(handle)))
+            nm = NativeModel(handle, sig, idx)
+            self._native[idx] = nm  # the stale one (if any) dies with its last holder
+            return nm
 
     def native_handle(self, device: torch.device):
-        """Pack (or re-pack after any weight change) the parameters into a native b2d_model."""
-        sig = (self._signature(), device.index)
-        if self._native is not None and self._native[0] == sig:
-            return self._native[1]
-        hp = self.hparams
-        hs = list(hp["hidden_sizes"])
-        uniform = all(h == hs[0] for h in hs)
-        ks, ss, pp = set(hp["kernel_sizes"]), set(hp["strides"]), set(hp["paddings"])
-        if not (uniform and len(ks) == 1 and len(ss) == 1 and len(pp) == 1):
-            raise NotImplementedError(f"GRUUNet2 (B200): non-uniform layer config is not implemented: {hp}")
-        cfg = _cabi.ModelConfig(hp["num_compressed_bins"], hs[0], len(hs), ks.pop(), ss.pop(), pp.pop(), hp["num_gaussians"])
-        params = [p.detach().to("cpu", torch.float32).contiguous() for p in self.parameters()]
-        offs = [g.gs.offset.detach().to("cpu", torch.float32).contiguous()
-                for g in (self.cell.input_gate, self.cell.reset_gate, self.cell.output_gate)]
-        parr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        oarr = (C.c_void_p * 3)(*[o.data_ptr() for o in offs])
-        handle = C.c_void_p()
-        with torch.cuda.device(device):
-            _cabi.check(_cabi.lib().b2d_model_create(C.byref(cfg), parr, len(params), oarr, C.byref(handle)))
-        if self._native is not None:
-            self._native[2]()  # destroy the stale native model now
-        fin = weakref.finalize(self, _cabi.lib().b2d_model_destroy, handle)
-        self._native = (sig, handle, fin)
-        return handle
-
-    def _apply(self, fn, *a, **k):  # .to()/.cuda() move the holders; the native pack follows lazily
-        return super()._apply(fn, *a, **k)
+        return self.native_model(device).handle
 
     # ---- forward (gruunet2.py:290-306) -------------------------------------------------------
     @torch.no_grad()
@@ -161,8 +189,12 @@ class GRUUNet2(nn.Module):
         if self.conv_mode not in CONV_MODES:
             raise ValueError(f"conv_mode must be one of {list(CONV_MODES)}, got {self.conv_mode!r}")
         lib = _cabi.lib()
-        handle = self.native_handle(x.device)
-        ws = self._ws.get(lib.b2d_gruunet2_workspace_bytes(handle, B, T), x.device)
+        native = self.native_model(x.device)  # held until the launches below are enqueued
+        handle = native.handle
+        # Re-entrant like the reference module (one model object is shared by every WebRTC session, app3.py:46,449): the
+        # packed weights are read-only and the scratch space is per call, taken from torch's stream-ordered caching
+        # allocator on the caller's current stream -- two threads / two streams never share it.
+        ws = torch.empty(max(int(lib.b2d_gruunet2_workspace_bytes(handle, B, T)), 256), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             _cabi.check(lib.b2d_gruunet2_forward(handle, x.data_ptr(), h.data_ptr(), out.data_ptr(), B, T,
                                                  CONV_MODES[self.conv_mode], ws.data_ptr(), ws.numel(), stream_ptr(x.device)))

@@ -10,6 +10,7 @@ that enqueues the kernel chain on the current CUDA stream.
 """
 from __future__ import annotations
 
+import threading
 from typing import Optional
 
 import numpy as np
@@ -17,8 +18,15 @@ import torch
 
 from . import _cabi
 from ._runtime import Workspace, draw_seed, get_plan, ptr, require_cuda_c64, require_cuda_f32, stream_ptr
-from .transforms import float_to_pcm16, pcm16_to_float
 from .gruunet2 import CONV_MODES, GRUUNet2
+
+
+def _indexed_device(device) -> torch.device:
+    """``cuda`` / None -> the current device with an explicit index, so device comparisons are exact."""
+    d = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if d.type != "cuda":
+        raise RuntimeError(f"audio_denoising_b200 runs on CUDA devices only, got {d}")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
 
 
 class DenoisePipeline:
@@ -33,11 +41,12 @@ class DenoisePipeline:
         self.model = model
         self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop_length, n_mels, sample_rate
         self.n_iter, self.momentum = n_iter, momentum
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = _indexed_device(device)
         self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device)
         if self.plan.rank < n_mels:
             raise ValueError(f"mel filterbank is rank deficient ({self.plan.rank} < {n_mels}) for n_fft={n_fft}, sample_rate={sample_rate}")
-        self._ws = Workspace()
+        self._ws = Workspace()  # one scratch buffer per CUDA stream the pipeline is used on
+        self._lock = threading.Lock()  # a call's launches are enqueued as one unit (threads sharing a stream share its scratch)
         self._host = None
 
     # -- shapes ---------------------------------------------------------------------------------
@@ -48,18 +57,39 @@ class DenoisePipeline:
         return self.plan.out_length(self.plan.num_frames(L))
 
     def _hx(self, hx, B, device):
+        shape = (B, self.model.latent_size, self.model.num_compressed_bins)
         if hx is None:
-            return torch.zeros(B, self.model.latent_size, self.model.num_compressed_bins, dtype=torch.float32, device=device)
-        return require_cuda_f32(hx, "hx").clone()
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        h = require_cuda_f32(hx, "hx")
+        if tuple(h.shape) != shape:
+            raise ValueError(f"hx must be {list(shape)} (batch, latent, compressed bins), got {list(h.shape)}")
+        if h.device != device:
+            raise ValueError(f"hx is on {h.device}, the input on {device}")
+        return h.clone()  # the reference never mutates the caller's hx
+
+    def _check_input(self, x: torch.Tensor, name: str):
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() != 2:
+            raise ValueError(f"{name} must be [B, L] (or [L]), got {list(x.shape)}")
+        if x.device != self.device:
+            raise ValueError(f"{name} is on {x.device} but this pipeline (plan, packed model) lives on {self.device}")
+        return x
+
+    def _check_out(self, out, B, Lout, dtype, device):
+        if out is None:
+            return torch.empty((B, Lout), dtype=dtype, device=device)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == device and out.dtype == dtype
+                and tuple(out.shape) == (B, Lout) and out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {dtype} tensor of shape [{B}, {Lout}] on {device}")
+        return out
 
     # -- app3 chain -----------------------------------------------------------------------------
     @torch.no_grad()
     def denoise(self, noisy: torch.Tensor, hx: Optional[torch.Tensor] = None, init_angles: Optional[torch.Tensor] = None,
                 normalise: bool = True, rand_init: bool = True, return_intermediates: bool = False, out: Optional[torch.Tensor] = None):
         """noisy [B, L] (CUDA float32) -> wave [B, hop*(T-1)] ; returns (wave, hx) or a dict."""
-        x = require_cuda_f32(noisy, "noisy")
-        if x.dim() == 1:
-            x = x.unsqueeze(0)
+        x = self._check_input(require_cuda_f32(noisy, "noisy"), "noisy")
         B, L = x.shape
         T = self.plan.num_frames(L)
         F = self.plan.n_freqs
@@ -68,42 +98,66 @@ class DenoisePipeline:
         seed = draw_seed() if (init_angles is None and rand_init) else 0  # TA functional.py:310, drawn in-kernel
         if init_angles is not None:
             init_angles = require_cuda_c64(init_angles, "init_angles").reshape(B, F, T)
-        wave = out if out is not None else torch.empty((B, self.plan.out_length(T)), dtype=torch.float32, device=dev)
+        wave = self._check_out(out, B, self.plan.out_length(T), torch.float32, dev)
         logmel = pred = mag = None
         if return_intermediates:
             logmel = torch.empty((B, T, self.n_mels), dtype=torch.float32, device=dev)
             pred = torch.empty_like(logmel)
             mag = torch.empty((B, T, self.plan.frame_stride), dtype=torch.float32, device=dev)
         lib = _cabi.lib()
-        handle = self.model.native_handle(dev)
-        ws = self._ws.get(lib.b2d_denoise_workspace_bytes(self.plan.handle, handle, B, L), dev)
-        with torch.cuda.device(dev):
+        native = self.model.native_model(dev)
+        with self._lock, torch.cuda.device(dev):
+            ws = self._ws.get(lib.b2d_denoise_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
             _cabi.check(lib.b2d_denoise_batch(
-                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
+                self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
                 1 if normalise else 0, CONV_MODES[self.model.conv_mode], wave.data_ptr(), ptr(logmel), ptr(pred), ptr(mag),
                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         if return_intermediates:
             return dict(wave=wave, hx=h, logmel=logmel.transpose(-1, -2), pred=pred, lin_mag=mag[..., :F].transpose(-1, -2))
         return wave, h
 
+    @torch.no_grad()
+    def denoise_pcm16(self, pcm: torch.Tensor, hx: Optional[torch.Tensor] = None, init_angles: Optional[torch.Tensor] = None,
+                      normalise: bool = True, rand_init: bool = True, out: Optional[torch.Tensor] = None):
+        """The same chain on the int16 PCM link of ``recv`` (app3.py:168-172 in, :244-245 out): pcm [B, L] int16 CUDA ->
+        (pcm_out [B, hop*(T-1)] int16, hx).  One native call; ``x = pcm / 32767`` is fused with the peak pass and the
+        float staging lives in the call's workspace -- nothing is allocated per call once the workspace exists."""
+        if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda and pcm.dtype == torch.int16):
+            raise TypeError("denoise_pcm16 expects an int16 CUDA tensor")
+        x = self._check_input(pcm.contiguous(), "pcm")
+        B, L = x.shape
+        T = self.plan.num_frames(L)
+        dev = x.device
+        h = self._hx(hx, B, dev)
+        seed = draw_seed() if (init_angles is None and rand_init) else 0
+        if init_angles is not None:
+            init_angles = require_cuda_c64(init_angles, "init_angles").reshape(B, self.plan.n_freqs, T)
+        res = self._check_out(out, B, self.plan.out_length(T), torch.int16, dev)
+        lib = _cabi.lib()
+        native = self.model.native_model(dev)
+        with self._lock, torch.cuda.device(dev):
+            ws = self._ws.get(lib.b2d_denoise_pcm16_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
+            _cabi.check(lib.b2d_denoise_batch_pcm16(
+                self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
+                1 if normalise else 0, CONV_MODES[self.model.conv_mode], res.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        return res, h
+
     # -- server chain -----------------------------------------------------------------------------
     @torch.no_grad()
     def denoise_noisy_phase(self, x: torch.Tensor, hx: Optional[torch.Tensor] = None, out_scale: float = 3.0, hx_decay: float = 0.9):
         """server.py:207-216: x [B, L] -> (wave [B, hop*(T-1)], hx) using the noisy phase."""
-        x = require_cuda_f32(x, "x")
-        if x.dim() == 1:
-            x = x.unsqueeze(0)
+        x = self._check_input(require_cuda_f32(x, "x"), "x")
         B, L = x.shape
         T = self.plan.num_frames(L)
         dev = x.device
         h = self._hx(hx, B, dev)
         wave = torch.empty((B, self.plan.out_length(T)), dtype=torch.float32, device=dev)
         lib = _cabi.lib()
-        handle = self.model.native_handle(dev)
-        ws = self._ws.get(lib.b2d_denoise_noisy_phase_workspace_bytes(self.plan.handle, handle, B, L), dev)
-        with torch.cuda.device(dev):
+        native = self.model.native_model(dev)
+        with self._lock, torch.cuda.device(dev):
+            ws = self._ws.get(lib.b2d_denoise_noisy_phase_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
             _cabi.check(lib.b2d_denoise_noisy_phase(
-                self.plan.handle, handle, x.data_ptr(), B, L, h.data_ptr(), float(out_scale), float(hx_decay),
+                self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), float(out_scale), float(hx_decay),
                 CONV_MODES[self.model.conv_mode], wave.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return wave, h
 
@@ -144,8 +198,10 @@ class DenoisePipeline:
             key = (hi - lo, L, noisy_host.dtype)
             ring = self._host["slots"].get(key)
             if ring is None:
+                # xin / res carry the link format (float32, or int16 PCM: half the bytes on the link); for int16 the float
+                # staging sits in the native call's workspace
                 ring = [dict(xin=torch.empty((hi - lo, L), dtype=noisy_host.dtype, device=dev),
-                             wave=torch.empty((hi - lo, Lout), dtype=torch.float32, device=dev),
+                             res=torch.empty((hi - lo, Lout), dtype=noisy_host.dtype, device=dev),
                              in_free=None, out_free=None) for _ in range(2)]
                 self._host["slots"][key] = ring
                 self._host["turn"][key] = 0
@@ -162,19 +218,14 @@ class DenoisePipeline:
                 compute.wait_event(slot["out_free"])  # ... and its result has left for the host
             ia = None if init_angles is None else init_angles[lo:hi]
             if pcm:
-                xf = pcm16_to_float(slot["xin"].reshape(-1)).reshape(slot["xin"].shape)
-                self.denoise(xf, init_angles=ia, rand_init=rand_init, out=slot["wave"])
-                result = float_to_pcm16(slot["wave"])
+                self.denoise_pcm16(slot["xin"], init_angles=ia, rand_init=rand_init, out=slot["res"])
             else:
-                self.denoise(slot["xin"], init_angles=ia, rand_init=rand_init, out=slot["wave"])
-                result = slot["wave"]
+                self.denoise(slot["xin"], init_angles=ia, rand_init=rand_init, out=slot["res"])
             slot["in_free"] = torch.cuda.Event()
             slot["in_free"].record(compute)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(slot["in_free"])
-                out_host[lo:hi].copy_(result, non_blocking=True)
-                if pcm:
-                    result.record_stream(d2h)
+                out_host[lo:hi].copy_(slot["res"], non_blocking=True)
                 slot["out_free"] = torch.cuda.Event()
                 slot["out_free"].record(d2h)
         if wait:
@@ -205,7 +256,7 @@ class StreamingDenoiser:
         self.model = model
         self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop_length, n_mels, sample_rate
         self.n_iter, self.momentum, self.S = n_iter, momentum, sessions
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = _indexed_device(device)
         self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device)
         if self.plan.rank < n_mels:
             raise ValueError(f"mel filterbank is rank deficient ({self.plan.rank} < {n_mels}) for n_fft={n_fft}, sample_rate={sample_rate}")
@@ -223,11 +274,13 @@ class StreamingDenoiser:
         self._seed_dev = torch.ones(1, dtype=torch.int64, device=self.device)
         self.use_graph = use_graph
         self._graph = None
+        self._side = None
+        self._graph_native = None  # the NativeModel whose device pointers the captured graph holds (kept alive with it)
 
     def _native_step(self, init, seed):
         lib = _cabi.lib()
         dev = self.device
-        handle = self.model.native_handle(dev)
+        handle = self.model.native_model(dev).handle
         ws = self._ws.get(lib.b2d_stream_step_workspace_bytes(self.plan.handle, handle, self.S), dev)
         with torch.cuda.device(dev):
             _cabi.check(lib.b2d_stream_step(
@@ -239,8 +292,11 @@ class StreamingDenoiser:
         """Capture one hop (H2D of the chunk and of the 8-byte seed, the whole kernel chain, D2H of the emitted hop) into a
         CUDA graph: a hop then costs one graph launch instead of ~45 kernel launches + 3 copies."""
         dev = self.device
+        native = self.model.native_model(dev)
         state = (self.hx.clone(), self.ola.clone())
-        side = torch.cuda.Stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)  # capture stream; its workspace entry is reused by a re-capture
+        side = self._side
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):  # warm-up: module loading, cudaFuncSetAttribute, workspace allocation
@@ -258,7 +314,7 @@ class StreamingDenoiser:
         self.hx.copy_(state[0])
         self.ola.copy_(state[1])
         torch.cuda.synchronize(dev)
-        self._graph = graph
+        self._graph, self._graph_native = graph, native
 
     @torch.no_grad()
     def step(self, window: np.ndarray) -> np.ndarray:
@@ -267,7 +323,9 @@ class StreamingDenoiser:
         self._chunk_host.numpy()[...] = window
         F = self.plan.n_freqs
         if self.angles_fn is None and self.use_graph:
-            if self._graph is None:
+            # the graph holds the packed model's device pointers: re-capture when the weights were re-packed
+            # (load_state_dict / optimizer.step / .to() on a live model); the old pack stays alive until then
+            if self._graph is None or self.model.native_model(dev) is not self._graph_native:
                 self._capture()
             self._seed_host[0] = draw_seed()
             self._graph.replay()

@@ -155,6 +155,15 @@ int b2d_denoise_batch(const b2d_plan* plan, const b2d_model* model, const float*
                       int normalise, int conv_mode, float* wave, float* logmel_bt, float* pred_bt, float* mag_tf,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the same chain on the int16 PCM link (what app3.py's recv exchanges: :168-172 in, :244-245 out) ----
+ * pcm [B, L] int16 -> x = pcm / 32767 (ingest fused with the peak pass) -> b2d_denoise_batch -> pcm_out [B, hop*(T-1)] int16
+ * = (clip(wave, -1, 1) * 32767) truncated toward zero.  The float staging lives in the workspace. */
+size_t b2d_denoise_pcm16_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L);
+int b2d_denoise_batch_pcm16(const b2d_plan* plan, const b2d_model* model, const short* pcm, int B, int L,
+                            float* hx, const b2d_c64* init_angles, unsigned long long seed, int n_iter, float momentum,
+                            int normalise, int conv_mode, short* pcm_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- server.py:207-216 chain (noisy-phase iSTFT, no Griffin-Lim) --------------------------------
  * x [B, L] -> wave [B, hop*(T-1)];  hx in/out and multiplied by hx_decay (0.9) afterwards. */
 size_t b2d_denoise_noisy_phase_workspace_bytes(const b2d_plan* plan, const b2d_model* model, int B, int L);

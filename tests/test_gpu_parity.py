@@ -734,3 +734,122 @@ def test_pipeline_other_geometries_match_oracle(dev, n_fft, L, B):
     b = metrics.si_sdr(ref["wave"], clean[:, :Lout])
     assert (a - b).abs().max() <= 0.05, (a.tolist(), b.tolist())
     assert metrics.si_sdr(r["wave"].cpu(), ref["wave"]).min() >= 40.0
+
+
+# ---------------------------------------------------------------------------------------------- round 2: host-layer contracts
+def test_denoise_pcm16_native_call_equals_float_chain(dev):
+    """b2d_denoise_batch_pcm16 (ingest fused with the peak pass, float staging in the workspace) is bit-identical to
+    pcm/32767 -> b2d_denoise_batch -> clip*32767: same kernels, same injected initial phase."""
+    import audio_denoising_b200 as adb
+
+    *_, synth = _oracle()
+    for B, L in [(3, 16000), (2, 16391)]:  # 16391: odd length -> unaligned rows, scalar ingest path
+        noisy, _ = synth.make_batch(B, L, 16000, start=150)
+        m, *_ = _our_model("good", dev)
+        pipe = adb.DenoisePipeline(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=16000)
+        T = 1 + L // 512
+        init = synth.gl_init_angles((B, 513, T), seed=5).to(dev)
+        pcm = (noisy * 0.8 * 32767).to(torch.int16).to(dev)
+        got, hx1 = pipe.denoise_pcm16(pcm, init_angles=init)
+        wave, hx2 = pipe.denoise(pcm.float() / 32767, init_angles=init)
+        want = (wave.clamp(-1, 1) * 32767).to(torch.int16)
+        assert got.dtype == torch.int16 and got.shape == want.shape
+        assert torch.equal(got, want)
+        assert torch.equal(hx1, hx2)
+        out = torch.empty_like(got)
+        r, _ = pipe.denoise_pcm16(pcm, init_angles=init, out=out)
+        assert r.data_ptr() == out.data_ptr() and torch.equal(out, want)
+
+
+def test_pipeline_validates_hx_out_and_device(dev):
+    """a stale hx from another batch size or a too-small / strided `out` must raise, not index out of bounds."""
+    import audio_denoising_b200 as adb
+
+    m, *_ = _our_model("good", dev)
+    pipe = adb.DenoisePipeline(m, n_fft=1024, hop_length=512, n_mels=64, sample_rate=16000, n_iter=2)
+    x = torch.randn(3, 8000, device=dev) * 0.1
+    Lout = pipe.out_length(8000)
+    with pytest.raises(ValueError):
+        pipe.denoise(x, hx=torch.zeros(2, 17, 4, device=dev))
+    with pytest.raises(ValueError):
+        pipe.denoise_noisy_phase(x, hx=torch.zeros(3, 17, 5, device=dev))
+    with pytest.raises(ValueError):
+        pipe.denoise(x, out=torch.empty(3, Lout - 1, device=dev))
+    with pytest.raises(ValueError):
+        pipe.denoise(x, out=torch.empty(3, 2 * Lout, device=dev)[:, ::2])
+    with pytest.raises(ValueError):
+        pipe.denoise(x, out=torch.empty(3, Lout, device=dev, dtype=torch.float16))
+    with pytest.raises(RuntimeError):
+        pipe.denoise(x.cpu())
+    w, h = pipe.denoise(x, hx=torch.zeros(3, 17, 4, device=dev), out=torch.empty(3, Lout, device=dev))
+    assert torch.isfinite(w).all() and h.shape == (3, 17, 4)
+
+
+def test_forward_is_reentrant_across_threads_and_streams(dev):
+    """One GRUUNet2 object shared by several sessions (app3.py:46,449): concurrent forwards on different CUDA streams from
+    different threads must not share scratch memory -- every result equals the single-threaded one bit for bit."""
+    import threading
+
+    m, *_ = _our_model("good", dev)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.rand(4 + i, 40 + 7 * i, 64, generator=g).to(dev) for i in range(4)]
+    want = [tuple(t.clone() for t in m(x)) for x in xs]
+    torch.cuda.synchronize()
+    got = [None] * len(xs)
+    errors = []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream(dev)
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    out, hx = m(xs[i])
+                s.synchronize()
+            got[i] = (out, hx)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(xs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for (o, h), (wo, wh) in zip(got, want):
+        assert torch.equal(o, wo) and torch.equal(h, wh)
+
+
+def test_streaming_graph_follows_weight_changes(dev):
+    """a captured hop must not keep replaying a freed / stale weight pack after load_state_dict on a live model."""
+    import audio_denoising_b200 as adb
+
+    sd_a, cfg = load_weights("good")
+    sd_b, _ = load_weights("dari_tult2")
+    rng = np.random.default_rng(5)
+    sig = (rng.standard_normal((1, 640 + 320 * 6)) * 0.1).astype(np.float32)
+
+    def run(states):
+        m = adb.GRUUNet2(**cfg)
+        m.load_state_dict(states[0])
+        m = m.to(dev).eval()
+        s = adb.StreamingDenoiser(m, n_fft=640, hop_length=320, n_mels=64, sample_rate=16000, n_iter=4, sessions=1,
+                                  angles_fn=None, use_graph=True)
+        torch.manual_seed(0)
+        outs = []
+        for i in range(6):
+            if i == 3 and len(states) > 1:
+                m.load_state_dict(states[1])
+            outs.append(s.step(sig[:, i * 320: i * 320 + 640]))
+        return np.concatenate(outs, axis=1), m
+
+    switched, m = run([sd_a, sd_b])
+    only_a, _ = run([sd_a])
+    assert np.array_equal(switched[:, : 3 * 320], only_a[:, : 3 * 320])  # same seeds, same weights for the first hops
+    assert not np.array_equal(switched[:, 3 * 320:], only_a[:, 3 * 320:])  # the new weights took effect in the graph
+    # explicit repack() after an edit autograd cannot see
+    h0 = m.native_model(dev)
+    assert m.native_model(dev) is h0
+    with torch.no_grad():
+        m.cell.input_gate.downs[0].conv.bias.data.add_(0.5)
+    m.repack()
+    assert m.native_model(dev) is not h0
