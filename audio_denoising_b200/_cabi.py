@@ -42,6 +42,7 @@ SIGNATURES = {
     "b2d_last_error_string": (C.c_char_p, []),
     "b2d_launch_count": (C.c_ulonglong, []),
     "b2d_plan_create": (_i, [_i, _i, _i, _vp, _vp, C.POINTER(_vp)]),
+    "b2d_plan_create_ex": (_i, [_i, _i, _i, _vp, _vp, C.c_uint, C.POINTER(_vp)]),
     "b2d_plan_destroy": (None, [_vp]),
     "b2d_plan_num_frames": (_i, [_vp, _i]),
     "b2d_plan_output_length": (_i, [_vp, _i]),

@@ -59,11 +59,16 @@ def melscale_fbanks_htk(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Te
     return torch.clamp(torch.minimum(rising, falling), min=0.0).contiguous()
 
 
-class Plan:
-    """Native DSP plan for one (n_fft, hop, n_mels, sample_rate) on one device."""
+# plan flags (include/b200denoise.h B2D_PLAN_*): fixed at plan creation, nothing on the compute path reads the environment
+PLAN_GENERIC_KERNELS, PLAN_EXACT_SQRT, PLAN_EXACT_UNIT, PLAN_EXACT_PEAK_DIV, PLAN_FP32_INVMEL = 1, 2, 4, 8, 16
+PLAN_EXACT_ALL = PLAN_EXACT_SQRT | PLAN_EXACT_UNIT | PLAN_EXACT_PEAK_DIV | PLAN_FP32_INVMEL
 
-    def __init__(self, n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.device):
-        self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop, n_mels, sample_rate
+
+class Plan:
+    """Native DSP plan for one (n_fft, hop, n_mels, sample_rate, flags) on one device."""
+
+    def __init__(self, n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.device, flags: int = 0):
+        self.n_fft, self.hop, self.n_mels, self.sample_rate, self.flags = n_fft, hop, n_mels, sample_rate, flags
         self.device = device
         self.n_freqs = n_fft // 2 + 1
         if n_mels == 0:  # STFT-only plan (Spectrogram / GriffinLim / InverseSpectrogram): dummy 1-column filterbank
@@ -84,7 +89,7 @@ class Plan:
         self.fb = fb
         handle = C.c_void_p()
         with torch.cuda.device(device):
-            _cabi.check(_cabi.lib().b2d_plan_create(n_fft, hop, max(n_mels, 1), fb.data_ptr(), pinv.data_ptr(), C.byref(handle)))
+            _cabi.check(_cabi.lib().b2d_plan_create_ex(n_fft, hop, max(n_mels, 1), fb.data_ptr(), pinv.data_ptr(), int(flags), C.byref(handle)))
         self.handle = handle
         self.frame_stride = _cabi.lib().b2d_plan_frame_stride(handle)
         weakref.finalize(self, _cabi.lib().b2d_plan_destroy, handle)
@@ -100,16 +105,16 @@ _plans: dict = {}
 _plans_lock = threading.Lock()
 
 
-def get_plan(n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.device) -> Plan:
+def get_plan(n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.device, flags: int = 0) -> Plan:
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError(f"audio_denoising_b200 plans live on CUDA devices, got {device}")
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (n_fft, hop, n_mels, sample_rate, idx)
+    key = (n_fft, hop, n_mels, sample_rate, idx, int(flags))
     with _plans_lock:
         p = _plans.get(key)
         if p is None:
-            p = Plan(n_fft, hop, n_mels, sample_rate, torch.device("cuda", idx))
+            p = Plan(n_fft, hop, n_mels, sample_rate, torch.device("cuda", idx), int(flags))
             _plans[key] = p
     return p
 

@@ -67,8 +67,13 @@ const char* b2d_last_error_string(void) { return last_error().c_str(); }
 unsigned long long b2d_launch_count(void) { return g_launches.load(); }
 
 int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, b2d_plan** out) {
+  return b2d_plan_create_ex(n_fft, hop, n_mels, h_mel_fb, h_pinv, 0u, out);
+}
+
+int b2d_plan_create_ex(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, unsigned flags, b2d_plan** out) {
   B2D_REQUIRE(out != nullptr, B2D_ERR_BAD_ARG, "out is NULL");
   *out = nullptr;
+  B2D_REQUIRE((flags & ~63u) == 0, B2D_ERR_BAD_ARG, "unknown plan flags 0x%x", flags);
   B2D_REQUIRE(n_fft >= 64 && n_fft <= 4096 && n_fft % 4 == 0, B2D_ERR_UNSUPPORTED,
               "n_fft must be a multiple of 4 in [64, 4096] (got %d)", n_fft);
   B2D_REQUIRE(hop >= 1 && hop <= n_fft, B2D_ERR_BAD_ARG, "hop must be in [1, n_fft] (got %d)", hop);
@@ -79,7 +84,7 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
 
   b2d_plan* p = new b2d_plan();
   memset(p, 0, sizeof(*p));
-  p->n_fft = n_fft; p->hop = hop; p->n_mels = n_mels;
+  p->n_fft = n_fft; p->hop = hop; p->n_mels = n_mels; p->flags = flags;
   p->M = n_fft / 2; p->F = p->M + 1; p->Fp = p->M + 4; p->fft = fd;
   B2D_CUDA(cudaGetDevice(&p->device));
   B2D_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
@@ -277,7 +282,7 @@ int b2d_inverse_mel_frames(const b2d_plan* plan, const float* mel_bt, int B, int
   B2D_REQUIRE(plan && mel_bt && mag_tf, B2D_ERR_BAD_ARG, "NULL pointer");
   B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "B and T must be >= 1");
   B2D_REQUIRE(aligned16(mag_tf) && aligned16(mel_bt), B2D_ERR_ALIGN, "mel_bt / mag_tf must be 16-byte aligned");
-  if (plan->d_tw8 != nullptr && getenv("B2D_INVMEL_FP32") == nullptr)
+  if (plan->d_tw8 != nullptr && !(plan->flags & B2D_PLAN_FP32_INVMEL))
     return launch_inverse_mel_tc(plan, mel_bt, (size_t)B * T, mag_tf, 3, ST(stream));
   return launch_inverse_mel(plan, mel_bt, B, T, mag_tf, false, ST(stream));
 }
@@ -371,7 +376,7 @@ static int denoise_chain(const b2d_plan* plan, const b2d_model* model, const flo
   if ((rc = launch_stft(plan, noisy, normalise ? w.peak : nullptr, B, L, logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(model, logmel, hx, pred, w.mel, 1, 0.f, B, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
   // inverse mel: tcgen05 GEMM (TF32 big/small split = fp32-class) when the plan has the weight images, else the CUDA-core SGEMM
-  if (plan->d_tw8 != nullptr) {
+  if (plan->d_tw8 != nullptr && !(plan->flags & B2D_PLAN_FP32_INVMEL)) {
     if ((rc = launch_inverse_mel_tc(plan, w.mel, (size_t)B * T, mag, 3, st))) return rc;
   } else if ((rc = launch_inverse_mel(plan, w.mel, B, T, mag, false, st))) {
     return rc;

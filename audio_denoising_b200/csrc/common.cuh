@@ -38,6 +38,20 @@ extern std::atomic<unsigned long long> g_launches;
       return ::b2d::fail(B2D_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory once per device (the attribute belongs to the function, not
+// to the launch): every launch site states its kernel here instead of calling cudaFuncSetAttribute per launch.
+#define B2D_SMEM_OPT_IN(...)                                                                                     \
+  do {                                                                                                           \
+    static std::atomic<unsigned long long> seen__{0};                                                            \
+    int dev__ = 0;                                                                                               \
+    cudaGetDevice(&dev__);                                                                                       \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                       \
+    if (!(seen__.load(std::memory_order_acquire) & bit__)) {                                                     \
+      B2D_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));          \
+      seen__.fetch_or(bit__, std::memory_order_release);                                                         \
+    }                                                                                                            \
+  } while (0)
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -54,6 +68,7 @@ struct FftDesc {  // passed by value to kernels
 
 struct b2d_plan {
   int n_fft, hop, n_mels, F, M, Fp;
+  unsigned flags;     // B2D_PLAN_* (include/b200denoise.h), fixed at creation
   b2d::FftDesc fft;
   int device;
   int num_sms;

@@ -437,7 +437,7 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                 float* logmel_bm, float2* spec, cudaStream_t st) {
   if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 && p->mel_seg_pad <= 320 && (long long)B * (1 + L / p->hop) < (1ll << 30) &&
-      getenv("B2D_STFT_GENERIC") == nullptr)
+      !(p->flags & B2D_PLAN_GENERIC_KERNELS))
     return launch_stft_fast512(p, wave, inv_scale, B, L, logmel_bt, st);
   StftArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.G = frames_per_block(p);
@@ -451,16 +451,16 @@ int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, in
   // a streaming hop is a single CTA per session: give it more threads; batches keep 256 (several CTAs per SM)
   const int threads = ((long)grid.x * grid.y <= 2 * p->num_sms) ? 512 : 256;
   if (p->M == 320) {
-    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(stft_kernel<320>);
     stft_kernel<320><<<grid, threads, smem, st>>>(a);
   } else if (p->M == 512) {
-    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(stft_kernel<512>);
     stft_kernel<512><<<grid, threads, smem, st>>>(a);
   } else if (p->M == 768) {
-    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(stft_kernel<768>);
     stft_kernel<768><<<grid, threads, smem, st>>>(a);
   } else {
-    B2D_CUDA(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(stft_kernel<0>);
     stft_kernel<0><<<grid, threads, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("stft_kernel");
@@ -485,11 +485,11 @@ int launch_inverse_mel(const b2d_plan* p, const float* mel, int B, int T, float*
   const int K = p->n_mels;
   const size_t smem = sizeof(float) * 2 * K * 68;
   if (torch_layout) {
-    B2D_CUDA(cudaFuncSetAttribute(inverse_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(inverse_mel_kernel<true>);
     dim3 grid((p->F + 63) / 64, (T + 63) / 64, B);
     inverse_mel_kernel<true><<<grid, 256, smem, st>>>(mel, p->d_pinv, out, B, T, K, p->F, p->Fp);
   } else {
-    B2D_CUDA(cudaFuncSetAttribute(inverse_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(inverse_mel_kernel<false>);
     const size_t NF = (size_t)B * T;
     dim3 grid((p->Fp + 63) / 64, (unsigned)((NF + 63) / 64), 1);
     inverse_mel_kernel<false><<<grid, 256, smem, st>>>(mel, p->d_pinv, out, B, T, K, p->F, p->Fp);
@@ -505,7 +505,7 @@ int launch_istft(const b2d_plan* p, const float2* spec, const float* mag, int B,
   a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.fd = p->fft;
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.inv_env = p->d_inv_env; a.wave = wave;
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * a.G * p->M) + 16;
-  B2D_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_SMEM_OPT_IN(istft_kernel);
   dim3 grid((T - 1 + a.G - 2) / (a.G - 1), B);
   istft_kernel<<<grid, 256, smem, st>>>(a);
   B2D_LAUNCH_CHECK("istft_kernel");

@@ -10,17 +10,16 @@ using namespace fast512;
 
 struct GlFastArgs {
   const float* mag_tf;   // [B,T,Fp]
-  float2* tprev;         // [B,T,M]
-  const float* xin;      // partial hop-block format (run = one warp's frames)
-  float* xout;
+  const float* xin;      // x_k, partial hop-block format (run = one warp's frames)
+  const float* xprev;    // x_{k-1}, same format (read only when USE_PREV)
+  float* xout;           // x_{k+1}
   int B, T, n, R, Fp;
   const float2* tw512;   // W512^k
   const float2* rtw;     // W1024^k, k = 0..511
   const float* win;      // [1024]
   const float* winn;     // [1024] win / N
   const float* inv_env;  // [512]
-  float mom;
-  int use_prev, store_prev;
+  float mom;             // momentum / (1 + momentum), TA functional.py:300
   // last iteration only: hop-blocks interior to a run are final -> written straight to the waveform
   float* wave;             // [B, HOP*(T-1)] or null
   const float* out_scale;  // [B] or null
@@ -54,31 +53,51 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// per-warp shared-memory staging: exchange buffer | tprev row | mag row | mbarrier
+// per-warp shared-memory staging
 constexpr int MAG_ROW_BYTES = (M + 4) * 4;                      // Fp floats = 2064 B
-constexpr int WARP_SMEM = XCH * 8 + M * 8 + 2080 + 16;          // 10800 B, 16-byte multiple
-constexpr int WARP_SMEM_X = WARP_SMEM + 2 * HOP * 4 + 16;       // + two hop-block buffers and their mbarriers (XTMA variant)
+constexpr int WARP_SMEM = XCH * 8 + M * 8 + 2080 + 16;          // init / STFT kernels: exchange | (unused row) | mag row | mbarrier
+// iteration kernel: exchange | mag row | mbarrier | ring of two slots, each [x_k hop-block | x_{k-1} hop-block] | two mbarriers
+constexpr int IT_OFF_MAG = XCH * 8;
+constexpr int IT_OFF_BAR = IT_OFF_MAG + 2080;
+constexpr int IT_OFF_RING = IT_OFF_BAR + 16;
+constexpr int IT_OFF_XBAR = IT_OFF_RING + 2 * 2 * HOP * 4;
+constexpr int IT_WARP_SMEM = IT_OFF_XBAR + 16;                  // 14912 B
+constexpr int IT_WARPS = 12;                                    // one persistent 12-warp CTA per SM (168 registers / thread)
 
-// same partial-format helpers as the generic kernel (griffinlim.cu); only used for the two reflect-padded
-// edge blocks of a clip (j == 0 and j == T), through a compact non-unrolled loop
-__device__ __noinline__ void stage_reflect_block(const float* __restrict__ part, const float* __restrict__ inv_env,
-                                                  const float* __restrict__ win_half, int b, int R, int n, int T, int j,
-                                                  float* __restrict__ dst, int lane) {
+// normalised (not yet windowed) sample `is` of interior hop-block js of clip b: the sum of the two partial slots on a run boundary
+__device__ __forceinline__ float partial_sample(const float* __restrict__ part, int b, int R, int n, int js, int is) {
+  const int r1 = (js - 1) / n, r2 = js / n;
+  float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
+  if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
+  return v;
+}
+// the two reflect-padded edge blocks of a clip (j == 0 and j == T), through a compact non-unrolled loop:
+// dst[i] = (x_k - mom * x_{k-1})[reflected index] * inv_env * win
+__device__ __noinline__ void stage_reflect_block(const float* __restrict__ part, const float* __restrict__ prev, float mom,
+                                                  const float* __restrict__ inv_env, const float* __restrict__ win_half, int b,
+                                                  int R, int n, int T, int j, float* __restrict__ dst, int lane) {
   for (int i = lane; i < HOP; i += 32) {
     int js, is;
     if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
     else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-    const int r1 = (js - 1) / n, r2 = js / n;
-    float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
-    if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
+    float v = partial_sample(part, b, R, n, js, is);
+    if (prev) v = fmaf(-mom, partial_sample(prev, b, R, n, js, is), v);
     dst[i] = v * inv_env[is] * win_half[i];
   }
 }
 
-template <int WARPS, int MINB, bool USE_PREV, bool XTMA, bool PERSIST>
-__global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFastArgs a) {
+// One fused Griffin-Lim iteration (TA:functional/functional.py:316-343) with the momentum term moved to the time domain.
+// The reference forms  angles = rebuilt_k - m * rebuilt_{k-1}  from two complex spectrograms; the STFT is linear, so
+//   rebuilt_k - m * rebuilt_{k-1} = STFT(x_k - m * x_{k-1}),
+// and only the DIRECTION of that difference is used.  The kernel therefore reads the two previous iterates (4 L bytes each)
+// instead of reading and writing a complex `tprev` (8 F T bytes each way): per clip and iteration
+//   read x_k, x_{k-1} (8 L) + mag (4 F T) + write x_{k+1} (4 L)  =  12 L + 4 F T   instead of   8 L + 20 F T,
+// 1.03 MB instead of 1.80 MB at config 2, with one forward and one inverse transform per frame as before.
+template <bool USE_PREV, bool EXACT>
+__global__ void __launch_bounds__(IT_WARPS * 32, 1) gl_fast512_kernel(const GlFastArgs a) {
+  constexpr int WARPS = IT_WARPS;
   // tables (float2 views): WA[256] = inv_env*win (first half), WB[256] = inv_env*win (second half),
-  // WN[512] = win/N, RT[512] = W1024^k ; per-warp exchange buffers behind them
+  // WN[512] = win/N, RT[512] = W1024^k ; per-warp buffers behind them
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* WA = reinterpret_cast<float2*>(smem_raw);
   float2* WB = WA + 256;
@@ -99,21 +118,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n, R = a.R, T = a.T;
   const int nruns = a.B * a.R;
-  // PERSIST: one CTA per SM; run ids are dealt round-robin over the CTAs first, so every SM carries the same number
-  // of busy warps (+-1).  Otherwise: consecutive warps of consecutive CTAs.
-  const int gw0 = PERSIST ? warp * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x * WARPS + warp;
-  const int gstep = PERSIST ? WARPS * (int)gridDim.x : nruns;
+  // one CTA per SM; run ids are dealt round-robin over the CTAs first, so every SM carries the same number of busy warps (+-1)
+  const int gw0 = warp * (int)gridDim.x + (int)blockIdx.x;
+  const int gstep = WARPS * (int)gridDim.x;
   if (gw0 >= nruns) return;
-  unsigned char* wsm = warp_base + (size_t)warp * (XTMA ? WARP_SMEM_X : WARP_SMEM);
+  unsigned char* wsm = warp_base + (size_t)warp * IT_WARP_SMEM;
   float2* S = reinterpret_cast<float2*>(wsm);                       // exchange buffer
-  float2* tp_s = reinterpret_cast<float2*>(wsm + XCH * 8);          // staged tprev row of the current frame
-  float* mg_s = reinterpret_cast<float*>(wsm + XCH * 8 + M * 8);    // staged mag row
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + XCH * 8 + M * 8 + 2080);
-  float* xs = reinterpret_cast<float*>(wsm + WARP_SMEM);            // XTMA: ring of two hop-blocks of the iterate
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(wsm + WARP_SMEM + 2 * HOP * 4);
+  float* mg_s = reinterpret_cast<float*>(wsm + IT_OFF_MAG);         // staged mag row of the current frame
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + IT_OFF_BAR);
+  float* xs = reinterpret_cast<float*>(wsm + IT_OFF_RING);          // ring slot s: x_k block at xs + s*2*HOP, x_{k-1} block behind it
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(wsm + IT_OFF_XBAR);
   if (lane == 0) {
     mbar_init(bar, 1);
-    if (XTMA) { mbar_init(xbar, 1); mbar_init(xbar + 1, 1); }
+    mbar_init(xbar, 1);
+    mbar_init(xbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -122,6 +140,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   // lane 0 owns families 0 and 32: its slots r >= 4 sit 224 bins below the regular lane + 64 r pattern
   const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
   const size_t run_stride = (size_t)(n + 1) * HOP;
+  const float2 nmom = make_float2(-a.mom, -a.mom);
+  constexpr uint32_t ring_bytes = (USE_PREV ? 2u : 1u) * HOP * 4u;
   uint32_t tma_uses = 0, xuse0 = 0, xuse1 = 0;  // completed phases of the three mbarriers (parity tracking across runs)
 
 #pragma unroll 1
@@ -129,28 +149,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
   const int b = gw / R, r = gw - b * R;
   const int tb = r * n, te = min(T, tb + n);
   const float* xrun = a.xin + (size_t)(b * R + r) * run_stride;
+  const float* prun = a.xprev + (size_t)(b * R + r) * run_stride;
   float* xo = a.xout + (size_t)(b * R + r) * run_stride;
   float2 carry[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
 
-  const uint32_t row_bytes = MAG_ROW_BYTES + (USE_PREV ? M * 8 : 0);
-  if (lane == 0) {  // TMA: rows of the first frame
-    mbar_expect_tx(bar, row_bytes);
+  if (lane == 0) {  // TMA: mag row of the first frame
+    mbar_expect_tx(bar, MAG_ROW_BYTES);
     bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, MAG_ROW_BYTES, bar);
-    if (USE_PREV) bulk_g2s(tp_s, a.tprev + ((size_t)b * T + tb) * M, M * 8, bar);
   }
   const int nrun = te - tb;
-  if (XTMA && lane == 0 && nrun > 1) {  // own-slot hop-blocks 1 .. nrun-1 travel by TMA, one frame ahead
-    mbar_expect_tx(xbar + 1, HOP * 4);
-    bulk_g2s(xs + HOP, xrun + HOP, HOP * 4, xbar + 1);
+  if (lane == 0 && nrun > 1) {  // own-slot hop-blocks 1 .. nrun-1 of both iterates travel by TMA, one frame ahead
+    mbar_expect_tx(xbar + 1, ring_bytes);
+    bulk_g2s(xs + 2 * HOP, xrun + HOP, HOP * 4, xbar + 1);
+    if (USE_PREV) bulk_g2s(xs + 3 * HOP, prun + HOP, HOP * 4, xbar + 1);
   }
 #pragma unroll 1
   for (int t = tb; t < te; ++t) {
     const int c = t - tb;
     float2 v[16];
-    if (!XTMA && t + 2 < te && lane < 16) prefetch_l2(xrun + (size_t)(c + 2) * HOP + lane * 32);  // next frame's new hop-block
-    // ---- stage the frame: hop-blocks t (first half) and t+1 (second half), envelope + window applied ---
+    // ---- stage the frame: d = x_k - m x_{k-1} on hop-blocks t (first half) and t+1 (second half), envelope + window applied ---
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = t + h;            // padded hop-block index
@@ -158,40 +177,49 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
       const float2* wtab = h ? WB : WA;
       if (j == 0 || j == T) {          // reflect-padded edge of the clip (2 blocks per clip): generic path via smem
         __syncwarp();
-        stage_reflect_block(a.xin, a.inv_env, a.win + h * HOP, b, R, n, T, j, reinterpret_cast<float*>(S), lane);
+        stage_reflect_block(a.xin, USE_PREV ? a.xprev : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, R, n, T, j,
+                            reinterpret_cast<float*>(S), lane);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[8 * h + q] = S[lane + 32 * q];
-      } else if (XTMA && cs >= 1 && cs <= nrun - 1) {  // interior block of this run: already in the shared-memory ring
+      } else if (cs >= 1 && cs <= nrun - 1) {  // interior block of this run: already in the shared-memory ring
         if (h == 1) {  // (h == 0: the same block was awaited one frame ago)
           if (cs & 1) { mbar_wait(xbar + 1, xuse1 & 1); ++xuse1; } else { mbar_wait(xbar, xuse0 & 1); ++xuse0; }
         }
-        const float2* src = reinterpret_cast<const float2*>(xs + (cs & 1) * HOP);
+        const float2* src = reinterpret_cast<const float2*>(xs + (cs & 1) * 2 * HOP);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float2 xv = src[lane + 32 * q];
-          const float2 wv = wtab[lane + 32 * q];
-          v[8 * h + q] = cscale2(xv, wv);
+          float2 xv = src[lane + 32 * q];
+          if (USE_PREV) xv = cfma2(src[256 + lane + 32 * q], nmom, xv);
+          v[8 * h + q] = cscale2(xv, wtab[lane + 32 * q]);
         }
       } else {
-        const float2* p1 = reinterpret_cast<const float2*>(xrun + (size_t)cs * HOP);
-        const float2* p2 = nullptr;   // second partial when the block sits on a run boundary
-        if (cs == 0) p2 = reinterpret_cast<const float2*>(xrun - run_stride + (size_t)n * HOP);   // previous run, last slot
-        else if (j == te) p2 = reinterpret_cast<const float2*>(xrun + run_stride);                // next run, slot 0
+        // block on a run boundary: the sum of this run's slot and the neighbouring run's slot
+        const size_t o1 = (size_t)cs * HOP;
+        const ptrdiff_t o2 = (cs == 0) ? -(ptrdiff_t)run_stride + (ptrdiff_t)n * HOP : (ptrdiff_t)run_stride;  // previous run's last slot / next run's slot 0
+        const bool two = (cs == 0) || (j == te);
+        const float2* p1 = reinterpret_cast<const float2*>(xrun + o1);
+        const float2* q1 = reinterpret_cast<const float2*>(prun + o1);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float2 xv = p1[lane + 32 * q];
-          if (p2) { const float2 x2 = p2[lane + 32 * q]; xv.x += x2.x; xv.y += x2.y; }
-          const float2 wv = wtab[lane + 32 * q];
-          v[8 * h + q] = cscale2(xv, wv);
+          if (two) xv = cadd(xv, reinterpret_cast<const float2*>(xrun + o2)[lane + 32 * q]);
+          if (USE_PREV) {
+            float2 pv = q1[lane + 32 * q];
+            if (two) pv = cadd(pv, reinterpret_cast<const float2*>(prun + o2)[lane + 32 * q]);
+            xv = cfma2(pv, nmom, xv);
+          }
+          v[8 * h + q] = cscale2(xv, wtab[lane + 32 * q]);
         }
       }
     }
-    if (XTMA) {  // block c is consumed: its buffer takes block c+2 while this frame computes
+    {  // block c is consumed: its ring slot takes block c+2 while this frame computes
       __syncwarp();
       if (lane == 0 && c + 2 <= nrun - 1) {
-        mbar_expect_tx(xbar + (c & 1), HOP * 4);
-        bulk_g2s(xs + (c & 1) * HOP, xrun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
+        float* slot = xs + (c & 1) * 2 * HOP;
+        mbar_expect_tx(xbar + (c & 1), ring_bytes);
+        bulk_g2s(slot, xrun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
+        if (USE_PREV) bulk_g2s(slot + HOP, prun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
       }
     }
     // ---- forward FFT ------------------------------------------------------------------------------------
@@ -203,8 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
     fwd2_store(lane, v, tw, S);
     __syncwarp();
     fwd3_load(lane, v, S);
-    // ---- spectral update (tprev / mag rows were bulk-copied into smem one frame ahead) -----------------------
-    float2* tp = a.tprev + ((size_t)b * T + t) * M;
+    // ---- projection to unit modulus, x mag (the mag row was bulk-copied into smem one frame ahead) ---------
     mbar_wait(bar, tma_uses & 1);
     ++tma_uses;
     if (lane == 0) lane0_permute(v);
@@ -213,23 +240,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) gl_fast512_kernel(const GlFa
       const int k = (rr < 4 ? kU0 : kU4) + 64 * rr;
       float2& U = v[2 * rr];
       float2& V = v[2 * (7 - rr) + 1];
-      if (rr == 0 && lane == 0) {
-        float2 x0M, x256;
-        special_update(U, V, USE_PREV ? tp_s[0] : make_float2(0.f, 0.f), USE_PREV ? tp_s[256] : make_float2(0.f, 0.f), mg_s[0], mg_s[M],
-                       mg_s[256], a.mom, USE_PREV, x0M, x256);
-        if (a.store_prev) { __stcs(tp, x0M); __stcs(tp + 256, x256); }
-      } else {
-        float2 xk, xmk;
-        pair_update(U, V, RT[k], USE_PREV ? tp_s[k] : make_float2(0.f, 0.f), USE_PREV ? tp_s[(M - k) & (M - 1)] : make_float2(0.f, 0.f),
-                    mg_s[k], mg_s[M - k], a.mom, USE_PREV, xk, xmk);
-        if (a.store_prev) { __stcs(tp + k, xk); __stcs(tp + (M - k), xmk); }
-      }
+      if (rr == 0 && lane == 0) special_project<EXACT>(U, V, mg_s[0], mg_s[M], mg_s[256]);
+      else pair_project<EXACT>(U, V, RT[k], mg_s[k], mg_s[M - k]);
     }
-    __syncwarp();  // every lane is done reading the staged rows
-    if (lane == 0 && t + 1 < te) {  // TMA: rows of the next frame land while this frame's inverse FFT runs
-      mbar_expect_tx(bar, row_bytes);
+    __syncwarp();  // every lane is done reading the staged row
+    if (lane == 0 && t + 1 < te) {  // TMA: mag row of the next frame lands while this frame's inverse FFT runs
+      mbar_expect_tx(bar, MAG_ROW_BYTES);
       bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + t + 1) * a.Fp, MAG_ROW_BYTES, bar);
-      if (USE_PREV) bulk_g2s(tp_s, a.tprev + ((size_t)b * T + t + 1) * M, M * 8, bar);
     }
     if (lane == 0) lane0_unpermute(v);
     // ---- inverse FFT ------------------------------------------------------------------------------------
@@ -382,7 +399,7 @@ int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, 
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
   constexpr int W = 8;
   const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
-  B2D_CUDA(cudaFuncSetAttribute(gl_fast512_init_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_SMEM_OPT_IN(gl_fast512_init_kernel<W>);
   gl_fast512_init_kernel<W><<<(B * R + W - 1) / W, W * 32, smem, st>>>(a);
   B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
   return B2D_OK;
@@ -403,6 +420,8 @@ struct StftFastArgs {
   const int* seg_first;   // [n_mels + 1]
   int seg_pad;
   float* logmel_bt;
+  int exact_sqrt;   // B2D_PLAN_EXACT_SQRT: IEEE square root for |X|
+  int exact_div;    // B2D_PLAN_EXACT_PEAK_DIV: x / peak as a division
 };
 
 __device__ __forceinline__ float sqrt_fast(float x) {
@@ -470,7 +489,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
 #pragma unroll 1
   for (; f < nframes; f += stride, slot ^= 1, b = bn, t = tn) {
     const float* x = a.wave + (size_t)b * a.L;
-    const float rsc = a.inv_scale ? 1.0f / a.inv_scale[b] : 1.0f;  // x / peak as x * (1 / peak): within one ulp of the division
+    const float pk = a.inv_scale ? a.inv_scale[b] : 1.0f;
+    const float rsc = 1.0f / pk;  // x / peak as x * (1 / peak): within one ulp of the division (exact_div: the division itself)
     float* cur = fbuf + slot * N;
     const float* src_cur;
     const bool cur_tma = interior(b, t, src_cur);
@@ -499,7 +519,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
       for (int q = 0; q < 16; ++q) {
         const float2 xv = c2[lane + 32 * q];
         const float2 wv = WIN[lane + 32 * q];
-        v[q] = cscale2(cscale2(xv, make_float2(rsc, rsc)), wv);
+        const float2 xn = a.exact_div ? make_float2(xv.x / pk, xv.y / pk) : cscale2(xv, make_float2(rsc, rsc));
+        v[q] = cscale2(xn, wv);
       }
     }
     __syncwarp();
@@ -519,12 +540,13 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
       if (rr == 0 && lane == 0) {
         Sf[0] = fabsf(U.x + U.y);
         Sf[M] = fabsf(U.x - U.y);
-        Sf[256] = sqrt_fast(V.x * V.x + V.y * V.y);
+        Sf[256] = a.exact_sqrt ? sqrtf(V.x * V.x + V.y * V.y) : sqrt_fast(V.x * V.x + V.y * V.y);
       } else {
         float2 xk, xmk;
         rfft_split(U, V, RT[k], xk, xmk);
-        Sf[k] = sqrt_fast(xk.x * xk.x + xk.y * xk.y);
-        Sf[M - k] = sqrt_fast(xmk.x * xmk.x + xmk.y * xmk.y);
+        const float s1 = xk.x * xk.x + xk.y * xk.y, s2 = xmk.x * xmk.x + xmk.y * xmk.y;
+        Sf[k] = a.exact_sqrt ? sqrtf(s1) : sqrt_fast(s1);
+        Sf[M - k] = a.exact_sqrt ? sqrtf(s2) : sqrt_fast(s2);
       }
     }
     if (lane < 8) Sf[M + 1 + lane] = 0.f;  // the zero-weight taps of a column's last segment read up to 7 bins past the Nyquist bin
@@ -558,10 +580,12 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win;
   a.seg_w = p->d_seg_w; a.seg_lo = p->d_seg_lo; a.seg_first = p->d_seg_first; a.seg_pad = p->mel_seg_pad;
   a.logmel_bt = logmel_bt;
+  a.exact_sqrt = (p->flags & B2D_PLAN_EXACT_SQRT) ? 1 : 0;
+  a.exact_div = (p->flags & B2D_PLAN_EXACT_PEAK_DIV) ? 1 : 0;
   constexpr int W = STFT_WARPS;
   B2D_REQUIRE(p->mel_seg_pad <= 320, B2D_ERR_UNSUPPORTED, "mel filterbank too dense for the n_fft = 1024 fast kernel");
   const size_t smem = sizeof(float2) * 1024 + (size_t)p->mel_seg_pad * 36 + sizeof(int) * ((p->n_mels + 4) & ~3) + (size_t)W * STFT_WSMEM;
-  B2D_CUDA(cudaFuncSetAttribute(stft_fast512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2D_SMEM_OPT_IN(stft_fast512_kernel);
   const size_t nframes = (size_t)B * a.T;
   const size_t want = (nframes + W - 1) / W;
   const int grid = (int)(want < (size_t)p->num_sms ? want : (size_t)p->num_sms);
@@ -570,48 +594,32 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   return B2D_OK;
 }
 
-template <int WARPS, int MINB, bool XTMA, bool PERSIST>
-static int launch_variant(const GlFastArgs& a, int num_sms, cudaStream_t st) {
-  const int runs = a.B * a.R;
-  const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)WARPS * (XTMA ? WARP_SMEM_X : WARP_SMEM);
-  const int ctas = (runs + WARPS - 1) / WARPS;
-  const dim3 grid(PERSIST ? (runs < num_sms ? runs : num_sms) : ctas), block(WARPS * 32);
-  if (a.use_prev) {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, true, XTMA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, true, XTMA, PERSIST><<<grid, block, smem, st>>>(a);
-  } else {
-    B2D_CUDA(cudaFuncSetAttribute(gl_fast512_kernel<WARPS, MINB, false, XTMA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gl_fast512_kernel<WARPS, MINB, false, XTMA, PERSIST><<<grid, block, smem, st>>>(a);
+int gl_fast_warps_per_sm() { return IT_WARPS; }
+
+template <bool USE_PREV, bool EXACT>
+static int launch_iteration(const GlFastArgs& a, int num_sms, cudaStream_t st) {
+  static bool configured = false;  // per instantiation; the attribute is a property of the function, set once per process
+  const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)IT_WARPS * IT_WARP_SMEM;
+  if (!configured) {
+    B2D_SMEM_OPT_IN(gl_fast512_kernel<USE_PREV, EXACT>);
+    configured = true;
   }
+  const int runs = a.B * a.R;
+  gl_fast512_kernel<USE_PREV, EXACT><<<runs < num_sms ? runs : num_sms, IT_WARPS * 32, smem, st>>>(a);
   B2D_LAUNCH_CHECK("gl_fast512_kernel");
   return B2D_OK;
 }
 
-int gl_fast_warps_per_sm() {
-  const char* e = getenv("B2D_GL_VARIANT");
-  const int v = e ? atoi(e) : 4;
-  return (v == 0 || v == 2) ? 16 : 12;
-}
-bool gl_fast_persistent() {
-  const char* e = getenv("B2D_GL_VARIANT");
-  return (e ? atoi(e) : 4) >= 4;
-}
-
-int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
-                      int n, int R, float mom, int use_prev, int store_prev, float* wave, const float* out_scale, cudaStream_t st) {
+int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, const float* xin, const float* xprev, float* xout, int B, int T,
+                      int n, int R, float mom, int use_prev, float* wave, const float* out_scale, cudaStream_t st) {
   GlFastArgs a;
-  a.mag_tf = mag_tf; a.tprev = tprev; a.xin = xin; a.xout = xout;
+  a.mag_tf = mag_tf; a.xin = xin; a.xprev = use_prev ? xprev : xin; a.xout = xout;
   a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
-  a.mom = mom; a.use_prev = use_prev; a.store_prev = store_prev; a.wave = wave; a.out_scale = out_scale;
-  const char* e = getenv("B2D_GL_VARIANT");
-  const int variant = e ? atoi(e) : 4;  // default: persistent, 12 warps/SM, tprev / mag / iterate all staged by TMA
-  if (variant == 1) return launch_variant<4, 3, false, false>(a, p->num_sms, st);   // 12 warps/SM, up to 168 registers
-  if (variant == 2) return launch_variant<4, 4, false, false>(a, p->num_sms, st);   // 16 warps/SM in 4-warp CTAs
-  if (variant == 0) return launch_variant<8, 2, false, false>(a, p->num_sms, st);   // 16 warps/SM in 8-warp CTAs
-  if (variant == 3) return launch_variant<6, 2, true, false>(a, p->num_sms, st);    // 12 warps/SM, iterate hop-blocks by TMA too
-  // (13+ warps per SM put 4 warps on one scheduler partition: 128-register cap -> spills, measured 107-120 us)
-  return launch_variant<12, 1, true, true>(a, p->num_sms, st);                      // one 12-warp CTA per SM, runs dealt evenly
+  a.mom = mom; a.wave = wave; a.out_scale = out_scale;
+  const bool exact = (p->flags & B2D_PLAN_EXACT_UNIT) != 0;
+  if (use_prev) return exact ? launch_iteration<true, true>(a, p->num_sms, st) : launch_iteration<true, false>(a, p->num_sms, st);
+  return exact ? launch_iteration<false, true>(a, p->num_sms, st) : launch_iteration<false, false>(a, p->num_sms, st);
 }
 
 }  // namespace b2d

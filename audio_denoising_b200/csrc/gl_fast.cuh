@@ -203,6 +203,42 @@ B2D_HD void pair_update(float2& U, float2& V, float2 rt, float2 pk, float2 pmk, 
   irfft_merge(make_float2(mk * uk.x, mk * uk.y), make_float2(mmk * umk.x, mmk * umk.y), rt, U, V);
 }
 
+// ---- time-domain-momentum form (gl_fast.cu): the transform input already is x_k - m x_{k-1}, so a pair slot only needs
+// split -> projection to unit modulus -> x mag -> merge.  EXACT: a / (|a| + 1e-16) with an IEEE square root and division,
+// exactly as TA:functional/functional.py:343 writes it (plan flag B2D_PLAN_EXACT_UNIT), instead of the reciprocal-square-
+// root unit.
+template <bool EXACT>
+B2D_HD float2 unit_dir_t(float2 a) {
+  if (EXACT) {
+    const float d = sqrtf(a.x * a.x + a.y * a.y) + 1e-16f;
+    return make_float2(a.x / d, a.y / d);
+  }
+  return unit_dir_fast(a);
+}
+template <bool EXACT>
+B2D_HD float unit_real_t(float a) {
+  if (EXACT) return a / (fabsf(a) + 1e-16f);
+  return a * inv_norm(a * a);
+}
+template <bool EXACT>
+B2D_HD void pair_project(float2& U, float2& V, float2 rt, float mk, float mmk) {
+  float2 xk, xmk;
+  rfft_split2(U, V, rt, xk, xmk);
+  if (EXACT) { xk = make_float2(0.5f * xk.x, 0.5f * xk.y); xmk = make_float2(0.5f * xmk.x, 0.5f * xmk.y); }  // the true X[k] next to the 1e-16
+  const float2 uk = unit_dir_t<EXACT>(xk), umk = unit_dir_t<EXACT>(xmk);
+  irfft_merge(make_float2(mk * uk.x, mk * uk.y), make_float2(mmk * umk.x, mmk * umk.y), rt, U, V);
+}
+// lane 0, slot 0: U = Z[0] (DC + Nyquist packed), V = Z[256] (self-paired bin M/2)
+template <bool EXACT>
+B2D_HD void special_project(float2& U, float2& V, float m0, float mM, float m256) {
+  const float X0 = U.x + U.y, XM = U.x - U.y;  // X[0], X[M] (real); X[256] = conj V
+  const float2 x256 = make_float2(V.x, -V.y);
+  const float y0 = m0 * unit_real_t<EXACT>(X0), yM = mM * unit_real_t<EXACT>(XM);
+  const float2 u = unit_dir_t<EXACT>(x256);
+  U = make_float2(y0 + yM, y0 - yM);
+  V = make_float2(2.0f * m256 * u.x, -2.0f * m256 * u.y);
+}
+
 // lane 0, slot 0: U = Z[0] (DC + Nyquist packed), V = Z[256] (self-paired bin M/2).
 // p0 = (Re P[0], Re P[M]) packed, p256 = P[256]; m0, mM, m256 magnitudes.  Returns packed rebuilt values.
 B2D_HD void special_update(float2& U, float2& V, float2 p0, float2 p256, float m0, float mM, float m256, float mom,

@@ -1,6 +1,8 @@
-// griffinlim.cu -- K6: fused fast Griffin-Lim iteration (TA:functional/functional.py:255-353).
+// griffinlim.cu -- K6: fused fast Griffin-Lim iteration (TA:functional/functional.py:255-353): the dispatcher (gl_run), the
+// generic shared-memory kernel (any n_fft / 2 = 2^a 3^b 5^c, the cross-check engine and the single-launch streaming mode)
+// and the stitch kernel.  The register / TMA fast paths live in gl_fast*.cu and gl_warp.cu.
 //
-// One launch = one iteration.  The launch reads the current time-domain iterate x_k, and per frame
+// Generic kernel: one launch = one iteration.  The launch reads the current time-domain iterate x_k, and per frame
 //   rebuilt = rfft(window * x_k)                      (torch.stft, center/reflect)
 //   a       = rebuilt - m * tprev ; a /= |a| + 1e-16  (momentum + projection to unit modulus)
 //   tprev   = rebuilt                                 (in place; each frame has one owner)
@@ -262,11 +264,9 @@ __global__ void __launch_bounds__(256) gl_stitch_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T,
-                      int n, int R, float mom, int use_prev, int store_prev, float* wave, const float* out_scale,
-                      cudaStream_t st);  // gl_fast.cu
+int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, const float* xin, const float* xprev, float* xout, int B, int T,
+                      int n, int R, float mom, int use_prev, float* wave, const float* out_scale, cudaStream_t st);  // gl_fast.cu
 int gl_fast_warps_per_sm();
-bool gl_fast_persistent();
 int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
                         int R, float mom, int use_prev, int store_prev, cudaStream_t st);  // gl_fast_n512.cu
 int launch_gl_fast_n2048(const b2d_plan* p, const float* mag_tf, float2* tprev, const float* xin, float* xout, int B, int T, int n,
@@ -305,63 +305,38 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   q.fast = 0;
   // a clip of at most one group of frames (a streaming hop: T = 3) runs init + all iterations in ONE launch of the generic
   // kernel, one CTA per clip: faster than 33 launches of the register kernels (n_fft 1024: 0.41 -> 0.3 ms per hop)
-  if (T <= q.G && getenv("B2D_GL_NO_FUSE") == nullptr) return generic_partition(p, B, T);
-  if (getenv("B2D_GL_GENERIC") == nullptr) {
+  if (T <= q.G) return generic_partition(p, B, T);
+  if (!(p->flags & B2D_PLAN_GENERIC_KERNELS)) {
     if (p->n_fft == 1024 && p->hop == 512) q.fast = 1;
     if (p->n_fft == 512 && p->hop == 256) q.fast = 2;
     if (p->n_fft == 2048 && p->hop == 1024) q.fast = 3;
     // every other length with hop = n_fft / 2 (640, 1536 ...): warp-synchronous Stockham kernel (gl_warp.cu)
-    if (!q.fast && gl_warp_supported(p) && getenv("B2D_GL_NO_WARP") == nullptr) q.fast = 4;
+    if (!q.fast && gl_warp_supported(p)) q.fast = 4;
   }
   if (q.fast) {
-    // one warp per run.  Pick the number of runs per clip R that minimises the busiest SM's load
-    // (runs per SM x frames per run), preferring a single round with at least 9 busy warps per SM.
+    // One warp per run, persistent CTAs.  Measured: a warp needs about the same time per frame whether 1 or 12 warps share
+    // the SM (the kernels are latency-bound per warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).
+    // Pick the number of runs per clip that minimises that; ties -> longer runs (less boundary traffic).
+    // (Measured dead ends, round 1: dealing the runs longest-first in serpentine order, and a balanced run table of equal
+    //  shares split at clip boundaries -- both correct, both 4-10 % slower: 1536 busy warps already saturate the SMs' issue /
+    //  shared-memory throughput, more runs only add boundary traffic.)
     const int wps = q.fast == 3 ? gl_fast_n2048_warps() : q.fast == 4 ? gl_warp_warps(p) : gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
-    const char* mn = getenv("B2D_GL_MIN_RUN");
-    const int min_run = mn ? (atoi(mn) < 1 ? 1 : atoi(mn)) : 2;  // frames per run: short runs cut the latency of small batches
+    const int min_run = 2;  // frames per run: short runs cut the latency of small batches
     const int maxR = (T + min_run - 1) / min_run;
-    if (gl_fast_persistent() || q.fast >= 2) {
-      // Measured: a warp needs ~4.5 us per frame whether 1 or 12 warps share the SM (the kernel is latency-bound per
-      // warp), so a launch lasts (rounds of runs per warp slot) x (frames per run).  Minimise that; ties -> longer runs
-      // (less boundary traffic).
-      // (Measured dead end: dealing the runs longest-first in serpentine order with an exact busiest-slot cost model picks
-      //  n = 20, R = 7 for config 2 -- every slot busy, 20 frames on the busiest instead of 21 -- and is 3.7 % slower; the
-      //  reordered schedule alone costs 3-5 %: with all slots busy the launch is throughput-bound, the extra run boundary
-      //  per clip costs traffic, and runs of one clip that are not walked at the same time lose their shared hop-blocks in L2.)
-      // (Second measured dead end: a balanced run table -- the flattened B x T frames cut into 1776 equal shares of 18-19
-      //  frames, split at clip boundaries, runs stored back to back so boundary partial sums are adjacent blocks -- was
-      //  correct but slower: 97.5 us instead of 88.4 us at B = 256, 375 instead of 310 us at B = 1024.  Filling every warp slot
-      //  does not help because 1536 busy warps already saturate the SMs' issue / shared-memory throughput; it only adds
-      //  run boundaries and table look-ups at the head of every run.)
-      long best = -1; int bestR = 1;
-      int bestN = T;
-      for (int R = 1; R <= maxR; ++R) {
-        int n = (T + R - 1) / R;
-        if (q.fast == 2) n = (n + 1) & ~1;  // n_fft 512 walks a run two frames at a time
-        const int Reff = (T + n - 1) / n;
-        const long runs = (long)B * Reff;
-        const long rounds = (runs + slots - 1) / slots;
-        const long cost = rounds * ((q.fast == 2 ? n / 2 : n) + 1);  // + 1: a run's fixed cost (first rows, boundary blocks, carry flush)
-        if (best < 0 || cost < best) { best = cost; bestR = Reff; bestN = n; }
-      }
-      if (const char* fn = getenv("B2D_GL_RUN")) {  // experiments: force the run length
-        int n = atoi(fn);
-        if (n >= 1 && n <= T) {
-          if (q.fast == 2) n = (n + 1) & ~1;
-          bestN = n;
-          bestR = (T + n - 1) / n;
-        }
-      }
-      q.n = bestN;
-      q.R = bestR;
-      return q;
+    long best = -1; int bestR = 1;
+    int bestN = T;
+    for (int R = 1; R <= maxR; ++R) {
+      int n = (T + R - 1) / R;
+      if (q.fast == 2) n = (n + 1) & ~1;  // n_fft 512 walks a run two frames at a time
+      const int Reff = (T + n - 1) / n;
+      const long runs = (long)B * Reff;
+      const long rounds = (runs + slots - 1) / slots;
+      const long cost = rounds * ((q.fast == 2 ? n / 2 : n) + 1);  // + 1: a run's fixed cost (first rows, boundary blocks, carry flush)
+      if (best < 0 || cost < best) { best = cost; bestR = Reff; bestN = n; }
     }
-    int R = (int)(slots / B);
-    if (R < 1) R = 1;
-    if (R > maxR) R = maxR;
-    q.n = (T + R - 1) / R;
-    q.R = (T + q.n - 1) / q.n;
+    q.n = bestN;
+    q.R = bestR;
     return q;
   }
   return generic_partition(p, B, T);
@@ -371,10 +346,12 @@ static size_t part_floats(const b2d_plan* p, const GlPartition& q, int B) {
   return (size_t)B * q.R * (q.n + 1) * p->hop;
 }
 
+// workspace: the n_fft = 1024 fast path keeps three time-domain iterates (x_{k-1}, x_k, x_{k+1}) and no spectrogram state;
+// the other kernels keep two iterates and the complex `tprev` [B, T, M]
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   const GlPartition q = gl_partition(p, B, T);
-  size_t bytes = 2 * align_up(part_floats(p, q, B) * sizeof(float), 256);
-  bytes += align_up((size_t)B * T * p->M * sizeof(float2), 256);
+  const size_t pbytes = align_up(part_floats(p, q, B) * sizeof(float), 256);
+  size_t bytes = (q.fast == 1) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
   if (need_mag_copy) bytes += align_up((size_t)B * T * p->Fp * sizeof(float), 256);
   return bytes;
 }
@@ -393,7 +370,8 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   unsigned char* base = static_cast<unsigned char*>(ws);
   float* xa = reinterpret_cast<float*>(base);
   float* xb = reinterpret_cast<float*>(base + pbytes);
-  float2* tprev = reinterpret_cast<float2*>(base + 2 * pbytes);
+  float* xc = reinterpret_cast<float*>(base + 2 * pbytes);       // fast == 1: third iterate
+  float2* tprev = reinterpret_cast<float2*>(base + 2 * pbytes);  // otherwise: complex spectrogram state
 
   GlArgs a;
   a.mag_tf = mag_tf; a.angles0 = init_angles; a.tprev = tprev;
@@ -402,53 +380,41 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = momentum / (1.0f + momentum);
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * q.G * p->M) + sizeof(float) * (size_t)((q.G + 2) * p->hop) + 16;
-  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2D_CUDA(cudaFuncSetAttribute(gl_generic_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int mt = (p->hop != p->M) ? 0 : (p->M == 320 || p->M == 512 || p->M == 768) ? p->M : 0;
-  auto launch_generic = [&](dim3 g, const GlArgs& args) {
+  auto launch_generic = [&](dim3 g, const GlArgs& args) -> int {
     int threads = p->M >= 640 ? 512 : 256;  // batch mode, measured at B = 256: n_fft 1536 1259 -> 1128 us per iteration with 512
-    if (const char* gt = getenv("B2D_GL_GENERIC_THREADS")) {
-      threads = atoi(gt);
-      if (threads < 32 || threads > 1024 || (threads & 31)) threads = 256;
-    }
-    if (args.fused_iters >= 0) {
-      // one CTA walks all the steps of a short clip alone: give it the whole SM (measured per-hop latency, n_fft 640 /
-      // 1536: 0.222 / 0.579 ms with 256 threads, 0.207 / 0.371 with 512, 0.211 / 0.357 with 1024)
-      threads = p->M >= 640 ? 1024 : (p->M >= 256 ? 512 : 256);
-      const char* ft = getenv("B2D_GL_FUSED_THREADS");
-      if (ft) threads = atoi(ft);
-      if (threads < 32 || threads > 1024 || (threads & 31)) threads = 256;
-    }
-    if (mt == 320) gl_generic_kernel<320><<<g, threads, smem, st>>>(args);
-    else if (mt == 768) gl_generic_kernel<768><<<g, threads, smem, st>>>(args);
-    else if (mt == 512) gl_generic_kernel<512><<<g, threads, smem, st>>>(args);
-    else gl_generic_kernel<0><<<g, threads, smem, st>>>(args);
+    // fused mode: one CTA walks all the steps of a short clip alone, give it the whole SM (measured per-hop latency, n_fft 640 /
+    // 1536: 0.222 / 0.579 ms with 256 threads, 0.207 / 0.371 with 512, 0.211 / 0.357 with 1024)
+    if (args.fused_iters >= 0) threads = p->M >= 640 ? 1024 : (p->M >= 256 ? 512 : 256);
+    if (mt == 320) { B2D_SMEM_OPT_IN(gl_generic_kernel<320>); gl_generic_kernel<320><<<g, threads, smem, st>>>(args); }
+    else if (mt == 768) { B2D_SMEM_OPT_IN(gl_generic_kernel<768>); gl_generic_kernel<768><<<g, threads, smem, st>>>(args); }
+    else if (mt == 512) { B2D_SMEM_OPT_IN(gl_generic_kernel<512>); gl_generic_kernel<512><<<g, threads, smem, st>>>(args); }
+    else { B2D_SMEM_OPT_IN(gl_generic_kernel<0>); gl_generic_kernel<0><<<g, threads, smem, st>>>(args); }
+    return B2D_OK;
   };
   dim3 grid(q.R, B);
   a.fused_iters = -1; a.xa = xa; a.xb = xb;
   float* cur = xa;
   float* nxt = xb;
+  float* prv = xc;
   bool direct_interior = false;
-  if (!q.fast && q.R == 1 && T <= 16 && getenv("B2D_GL_NO_FUSE") == nullptr) {
+  int rc;
+  if (!q.fast && q.R == 1 && T <= 16) {
     // short clips (streaming hops: T = 3): every dependency stays inside one CTA -> init + all iterations in one launch
     a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
     a.fused_iters = n_iter;
-    launch_generic(grid, a);
+    if ((rc = launch_generic(grid, a))) return rc;
     B2D_LAUNCH_CHECK("gl_generic_kernel(fused)");
     cur = (n_iter & 1) ? xb : xa;  // step s writes xa when s is even; the last step is s = n_iter
   } else {
   // x_0 = istft(mag * angles_0)
   a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;
   if (q.fast == 1 && init_angles == nullptr) {
-    int rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
-    if (rc != B2D_OK) return rc;
+    if ((rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st))) return rc;
   } else if (q.fast == 3 && init_angles == nullptr) {
-    int rc = launch_gl_fast_n2048_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st);
-    if (rc != B2D_OK) return rc;
+    if ((rc = launch_gl_fast_n2048_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st))) return rc;
   } else {
-    launch_generic(grid, a);
+    if ((rc = launch_generic(grid, a))) return rc;
     B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
   }
   a.init = 0; a.angles0 = nullptr;
@@ -456,26 +422,23 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     a.use_prev = (it > 0 && a.mom != 0.f) ? 1 : 0;
     a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
     a.xin = cur; a.xout = nxt;
+    const bool last = (it + 1 == n_iter);  // last iteration: run-interior hop-blocks go straight to `wave`
     if (q.fast == 1) {
-      const bool last = (it + 1 == n_iter) && getenv("B2D_GL_NO_DIRECT") == nullptr;  // last iteration: run-interior hop-blocks go straight to `wave`
-      int rc = launch_gl_fast512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev,
-                                 last ? wave : nullptr, out_scale, st);
-      if (rc != B2D_OK) return rc;
+      // time-domain momentum: reads x_k (cur) and x_{k-1} (prv), writes x_{k+1} (nxt); three buffers rotate
+      if ((rc = launch_gl_fast512(p, mag_tf, cur, prv, nxt, B, T, q.n, q.R, a.mom, a.use_prev, last ? wave : nullptr, out_scale, st))) return rc;
       direct_interior = last;
+      float* t = prv; prv = cur; cur = nxt; nxt = t;
+      continue;
     } else if (q.fast == 2) {
-      int rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
-      if (rc != B2D_OK) return rc;
+      if ((rc = launch_gl_fast_n512(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st))) return rc;
     } else if (q.fast == 4) {
-      int rc = launch_gl_warp(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st);
-      if (rc != B2D_OK) return rc;
+      if ((rc = launch_gl_warp(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev, st))) return rc;
     } else if (q.fast == 3) {
-      const bool last = (it + 1 == n_iter) && getenv("B2D_GL_NO_DIRECT") == nullptr;
-      int rc = launch_gl_fast_n2048(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev,
-                                    last ? wave : nullptr, out_scale, st);
-      if (rc != B2D_OK) return rc;
+      if ((rc = launch_gl_fast_n2048(p, mag_tf, tprev, cur, nxt, B, T, q.n, q.R, a.mom, a.use_prev, a.store_prev,
+                                     last ? wave : nullptr, out_scale, st))) return rc;
       direct_interior = last;
     } else {
-      launch_generic(grid, a);
+      if ((rc = launch_generic(grid, a))) return rc;
       B2D_LAUNCH_CHECK("gl_generic_kernel");
     }
     float* t = cur; cur = nxt; nxt = t;

@@ -109,9 +109,13 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encoder_kernel(const float* __
 // ------------------------------------------------------------------------------------------------
 // Gate non-linearities on the exp2 unit (ex2.approx has 2 ulp of error, the reciprocal 1 ulp: ~3e-7 relative, far inside
 // the 1e-5 model parity budget); tanh(v) = 1 - 2 / (1 + e^{2v}) saturates cleanly to +-1 when the exponential overflows / underflows.
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float tanhf_(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+// EXACT (B2D_CONV_EXACT_GATES): expf and IEEE division -- the attribution switch of test_exact_math_attribution.
+template <bool EXACT>
+__device__ __forceinline__ float sigmoidf_(float v) { return EXACT ? 1.0f / (1.0f + expf(-v)) : __fdividef(1.0f, 1.0f + __expf(-v)); }
+template <bool EXACT>
+__device__ __forceinline__ float tanhf_(float v) { return EXACT ? tanhf(v) : 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict__ blob, const float* __restrict__ gx,
                                                         float* __restrict__ hx, float* __restrict__ hseq, int T) {
   const Packed L = packed_layout();
@@ -173,9 +177,9 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
     const float sr = fmaxf(ar[0] + ar[1] + ar[2], 0.f);  // both pre-activations went through ReLU (gruunet2.py:71-79, Q8)
     const float sz = fmaxf(az[0] + az[1] + az[2], 0.f);
     const float sn = fmaxf(an[0] + an[1] + an[2], 0.f);
-    const float z = sigmoidf_(xz + sz);
-    const float r = sigmoidf_(xr + sr);
-    const float nw = tanhf_(xn + r * sn);
+    const float z = sigmoidf_<EXACT>(xz + sz);
+    const float r = sigmoidf_<EXACT>(xr + sr);
+    const float nw = tanhf_<EXACT>(xn + r * sn);
     const float hn = nw + z * (h - nw);
     if (active) {
       hp[(t + 1) & 1][c][j + 1] = hn;  // the other buffer: nobody reads it during this step
@@ -504,8 +508,10 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
                   float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "GRUUNet2 forward needs B >= 1 and T >= 1 (got %d, %d)", B, T);
   B2D_REQUIRE(ws != nullptr && ws_bytes >= model_workspace_bytes(m, B, T), B2D_ERR_WORKSPACE, "GRUUNet2 workspace too small");
+  const bool exact_gates = (conv_mode & B2D_CONV_EXACT_GATES) != 0;
+  conv_mode &= 0xff;
   B2D_REQUIRE(conv_mode >= 0 && conv_mode <= 4, B2D_ERR_BAD_ARG, "conv_mode must be in [0, 4]");
-  const bool fma_encoder = (conv_mode == 0) || (conv_mode >= 3 && getenv("B2D_MMA_ENCODER_OFF") != nullptr);
+  const bool fma_encoder = (conv_mode == 0);
   const size_t nf = (size_t)B * T;
   unsigned char* base = static_cast<unsigned char*>(ws);
   float* d0 = reinterpret_cast<float*>(base); base += align_up(nf * D0 * 4, 256);
@@ -519,7 +525,7 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess || dev_sms < 1) dev_sms = 148;
   if (fma_encoder) {
     const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
-    B2D_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(encoder_kernel);
     const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
     const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
     encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
@@ -531,7 +537,8 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
     int rc = model_forward_tc(m, x, nf, d0, d1, d2, gx, conv_mode, st);
     if (rc != B2D_OK) return rc;
   }
-  recurrence_kernel<<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
+  if (exact_gates) recurrence_kernel<true><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
+  else recurrence_kernel<false><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
   B2D_LAUNCH_CHECK("recurrence_kernel");
   if (conv_mode >= 3) {
     int rc = model_decode_mma(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode == 3 ? 3 : 1, dev_sms, st);
@@ -539,7 +546,7 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   } else if (conv_mode == 0) {
     const int nw = L.total - L.dec_w[0];
     const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC2_WARPS * DEC2_FW * DEC2_FR);
-    B2D_CUDA(cudaFuncSetAttribute(decoder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2D_SMEM_OPT_IN(decoder2_kernel);
     const size_t want = (nf + DEC2_WARPS * DEC2_FW - 1) / (DEC2_WARPS * DEC2_FW);
     const int grid = (int)(want < (size_t)dev_sms * 2 ? want : (size_t)dev_sms * 2);
     decoder2_kernel<<<grid, DEC2_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);

@@ -91,8 +91,8 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
   B2D_LAUNCH_CHECK("stream_pre_kernel");
   if ((rc = launch_stft(p, w.x, nullptr, S, N, w.logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(m, w.logmel, hx, w.pred, w.mel, 1, 0.f, S, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
-  if (p->d_tw8 != nullptr) {
-    if ((rc = launch_inverse_mel_tc(p, w.mel, (size_t)S * T, w.mag, conv_mode == 2 ? 1 : 3, st))) return rc;
+  if (p->d_tw8 != nullptr && !(p->flags & B2D_PLAN_FP32_INVMEL)) {
+    if ((rc = launch_inverse_mel_tc(p, w.mel, (size_t)S * T, w.mag, 3, st))) return rc;
   } else if ((rc = launch_inverse_mel(p, w.mel, S, T, w.mag, false, st))) {
     return rc;
   }

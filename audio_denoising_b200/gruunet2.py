@@ -98,6 +98,7 @@ class GRUUNet2(nn.Module):
         self.num_compressed_bins = num_compressed_bins
         self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
         self.conv_mode = "mma"  # one of CONV_MODES
+        self.exact_gates = False  # attribution switch: GRU gates through expf / IEEE division (B2D_CONV_EXACT_GATES)
         self._native = {}  # device index -> NativeModel
         self._native_lock = threading.Lock()
         self._generation = 0  # bumped by repack()
@@ -165,6 +166,12 @@ class GRUUNet2(nn.Module):
     def native_handle(self, device: torch.device):
         return self.native_model(device).handle
 
+    def native_conv_mode(self) -> int:
+        """The ``conv_mode`` word of the C-ABI: engine in the low byte, B2D_CONV_EXACT_GATES (0x100) or-ed in."""
+        if self.conv_mode not in CONV_MODES:
+            raise ValueError(f"conv_mode must be one of {list(CONV_MODES)}, got {self.conv_mode!r}")
+        return CONV_MODES[self.conv_mode] | (0x100 if self.exact_gates else 0)
+
     # ---- forward (gruunet2.py:290-306) -------------------------------------------------------
     @torch.no_grad()
     def forward(self, input: torch.Tensor, hx: Optional[torch.Tensor] = None):
@@ -186,8 +193,7 @@ class GRUUNet2(nn.Module):
         out = torch.empty_like(x)
         if T == 0:
             return (out.squeeze(0) if two_dimmed else out), h
-        if self.conv_mode not in CONV_MODES:
-            raise ValueError(f"conv_mode must be one of {list(CONV_MODES)}, got {self.conv_mode!r}")
+        mode = self.native_conv_mode()
         lib = _cabi.lib()
         native = self.native_model(x.device)  # held until the launches below are enqueued
         handle = native.handle
@@ -197,7 +203,7 @@ class GRUUNet2(nn.Module):
         ws = torch.empty(max(int(lib.b2d_gruunet2_workspace_bytes(handle, B, T)), 256), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             _cabi.check(lib.b2d_gruunet2_forward(handle, x.data_ptr(), h.data_ptr(), out.data_ptr(), B, T,
-                                                 CONV_MODES[self.conv_mode], ws.data_ptr(), ws.numel(), stream_ptr(x.device)))
+                                                 mode, ws.data_ptr(), ws.numel(), stream_ptr(x.device)))
         if two_dimmed:
             out = out.squeeze(0)
         return out, h

@@ -31,7 +31,7 @@ def _indexed_device(device) -> torch.device:
 
 class DenoisePipeline:
     def __init__(self, model: GRUUNet2, n_fft: int = 1024, hop_length: int = 512, n_mels: int = 64, sample_rate: int = 16000,
-                 n_iter: int = 32, momentum: float = 0.99, device: Optional[torch.device] = None):
+                 n_iter: int = 32, momentum: float = 0.99, device: Optional[torch.device] = None, plan_flags: int = 0):
         if not isinstance(model, GRUUNet2):
             raise TypeError("model must be an audio_denoising_b200.GRUUNet2")
         if n_mels != model.n_mels:
@@ -42,7 +42,7 @@ class DenoisePipeline:
         self.n_fft, self.hop, self.n_mels, self.sample_rate = n_fft, hop_length, n_mels, sample_rate
         self.n_iter, self.momentum = n_iter, momentum
         self.device = _indexed_device(device)
-        self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device)
+        self.plan = get_plan(n_fft, hop_length, n_mels, sample_rate, self.device, plan_flags)  # flags: _runtime.PLAN_*
         if self.plan.rank < n_mels:
             raise ValueError(f"mel filterbank is rank deficient ({self.plan.rank} < {n_mels}) for n_fft={n_fft}, sample_rate={sample_rate}")
         self._ws = Workspace()  # one scratch buffer per CUDA stream the pipeline is used on
@@ -110,7 +110,7 @@ class DenoisePipeline:
             ws = self._ws.get(lib.b2d_denoise_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
             _cabi.check(lib.b2d_denoise_batch(
                 self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
-                1 if normalise else 0, CONV_MODES[self.model.conv_mode], wave.data_ptr(), ptr(logmel), ptr(pred), ptr(mag),
+                1 if normalise else 0, self.model.native_conv_mode(), wave.data_ptr(), ptr(logmel), ptr(pred), ptr(mag),
                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         if return_intermediates:
             return dict(wave=wave, hx=h, logmel=logmel.transpose(-1, -2), pred=pred, lin_mag=mag[..., :F].transpose(-1, -2))
@@ -139,7 +139,7 @@ class DenoisePipeline:
             ws = self._ws.get(lib.b2d_denoise_pcm16_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
             _cabi.check(lib.b2d_denoise_batch_pcm16(
                 self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), ptr(init_angles), seed, self.n_iter, float(self.momentum),
-                1 if normalise else 0, CONV_MODES[self.model.conv_mode], res.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+                1 if normalise else 0, self.model.native_conv_mode(), res.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return res, h
 
     # -- server chain -----------------------------------------------------------------------------
@@ -158,7 +158,7 @@ class DenoisePipeline:
             ws = self._ws.get(lib.b2d_denoise_noisy_phase_workspace_bytes(self.plan.handle, native.handle, B, L), dev)
             _cabi.check(lib.b2d_denoise_noisy_phase(
                 self.plan.handle, native.handle, x.data_ptr(), B, L, h.data_ptr(), float(out_scale), float(hx_decay),
-                CONV_MODES[self.model.conv_mode], wave.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+                self.model.native_conv_mode(), wave.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return wave, h
 
     # -- host-to-host (end-to-end) ----------------------------------------------------------------
@@ -285,7 +285,7 @@ class StreamingDenoiser:
         with torch.cuda.device(dev):
             _cabi.check(lib.b2d_stream_step(
                 self.plan.handle, handle, self._chunk_dev.data_ptr(), self.S, self.hx.data_ptr(), self.ola.data_ptr(), ptr(init), seed,
-                self._seed_dev.data_ptr(), self.n_iter, float(self.momentum), CONV_MODES[self.model.conv_mode], self._out_dev.data_ptr(),
+                self._seed_dev.data_ptr(), self.n_iter, float(self.momentum), self.model.native_conv_mode(), self._out_dev.data_ptr(),
                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
 
     def _capture(self):

@@ -58,6 +58,23 @@ const char* b2d_last_error_string(void);
  * setting the reference uses: app3.py:29-33, server.py:166-170).
  * n_fft must be even with n_fft/2 = 2^a 3^b 5^c and 64 <= n_fft <= 4096. */
 int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, b2d_plan** out);
+/* The same with option flags, fixed for the life of the plan (nothing on the compute path reads the environment):
+ * B2D_PLAN_GENERIC_KERNELS  every transform runs on the generic shared-memory Stockham kernels -- the cross-check engine
+ *                           the tests hold the register / TMA fast paths against;
+ * the B2D_PLAN_EXACT_* / FP32_* flags swap one approximation each for the exact operation the reference performs, so that
+ * tests/test_gpu_parity.py::test_exact_math_attribution can attribute the end-to-end deviation from the CPU oracle:
+ *   EXACT_SQRT      |STFT| with an IEEE square root instead of sqrt.approx.ftz (app3.py:192)
+ *   EXACT_UNIT      Griffin-Lim projection a / (|a| + 1e-16) with IEEE sqrt + division instead of rsqrt.approx (TA functional.py:343)
+ *   EXACT_PEAK_DIV  x / peak as a division instead of x * (1 / peak) (app3.py:183)
+ *   FP32_INVMEL     inverse mel as an fp32 FMA GEMM instead of the TF32x3 tcgen05 GEMM
+ * (GENERIC_KERNELS also forms the Griffin-Lim momentum term in the frequency domain from a stored complex `tprev`, literally
+ *  as TA functional.py:337-341 does; the n_fft = 1024 fast path forms it on the time-domain iterates, see csrc/gl_fast.cu.) */
+#define B2D_PLAN_GENERIC_KERNELS 1u
+#define B2D_PLAN_EXACT_SQRT 2u
+#define B2D_PLAN_EXACT_UNIT 4u
+#define B2D_PLAN_EXACT_PEAK_DIV 8u
+#define B2D_PLAN_FP32_INVMEL 16u
+int b2d_plan_create_ex(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, unsigned flags, b2d_plan** out);
 void b2d_plan_destroy(b2d_plan* plan);
 int b2d_plan_num_frames(const b2d_plan* plan, int L);     /* T = 1 + L / hop                 */
 int b2d_plan_output_length(const b2d_plan* plan, int T);  /* hop * (T - 1)  (length=None)    */
@@ -105,10 +122,12 @@ int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* m
 /* ---- K3: GRUUNet2.forward (gruunet2.py:290-306) -----------------------------------------------
  * x [B, T, n_mels], hx [B, hidden, bins] in/out (caller zero-fills it for hx=None), out [B, T, n_mels].
  * Runs encoder (time-parallel) -> persistent recurrence -> decoder (time-parallel).
- * conv_mode: 0 = fp32 CUDA-core convolutions, 1 = tcgen05/TMEM implicit GEMM with TF32 operands split into
+ * conv_mode (low byte): 0 = fp32 CUDA-core convolutions, 1 = tcgen05/TMEM implicit GEMM with TF32 operands split into
  * big + small parts (3 MMAs per k-step, fp32-class accuracy), 2 = tcgen05 single-pass TF32 (throughput mode),
  * 3 = decoder on warp-level m16n8k8 tensor-core MMAs with the same big + small split (fp32-class), 4 = the same, single pass.
- * In the fused chains conv_mode != 0 also runs the inverse-mel projection as a tcgen05 GEMM. */
+ * B2D_CONV_EXACT_GATES or-ed in: GRU gate sigmoid / tanh through expf and IEEE division instead of ex2.approx / rcp.approx
+ * (the reference's torch.sigmoid / torch.tanh, gruunet2.py:231-240) -- the model's switch for test_exact_math_attribution. */
+#define B2D_CONV_EXACT_GATES 0x100
 size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T);
 int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T,
                          int conv_mode, void* workspace, size_t workspace_bytes, void* stream);

@@ -9,16 +9,14 @@ dev = torch.device("cuda:0"); lib = _cabi.lib(); st = torch.cuda.current_stream(
 g = torch.Generator().manual_seed(1)
 for n_fft in (512, 1024, 2048):
     plan = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev)
+    plan_g = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev, flags=_runtime.PLAN_GENERIC_KERNELS)
     for B, T in [(2, 3126), (1, 18751), (3000, 4)]:
         mag = (torch.rand(B, T, plan.frame_stride, generator=g) * 2).to(dev)
-        ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(plan.handle, B, T), dtype=torch.uint8, device=dev)
         outs = []
-        for generic in (False, True):
-            if generic: os.environ["B2D_GL_GENERIC"] = "1"
-            else: os.environ.pop("B2D_GL_GENERIC", None)
-            wave = torch.zeros(B, plan.out_length(T), device=dev)
-            _cabi.check(lib.b2d_griffinlim_frames(plan.handle, mag.data_ptr(), None, 0, B, T, 2, 0.99, None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        for pl in (plan, plan_g):
+            ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(pl.handle, B, T), dtype=torch.uint8, device=dev)
+            wave = torch.zeros(B, pl.out_length(T), device=dev)
+            _cabi.check(lib.b2d_griffinlim_frames(pl.handle, mag.data_ptr(), None, 0, B, T, 2, 0.99, None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
             torch.cuda.synchronize(); outs.append(wave.cpu())
-        os.environ.pop("B2D_GL_GENERIC", None)
         s = metrics.si_sdr(outs[0], outs[1])
         print(n_fft, B, T, "median", round(float(s.median()), 1), "min", round(float(s.min()), 1), flush=True)

@@ -4,6 +4,9 @@ Run on the B200 box with ``pytest -m gpu``.  Tolerances (north_star): STFT / Mel
 (fp32); model fp32 mode rel-L2 <= 1e-5; Griffin-Lim with identical injected initial angles
 SI-SDR(ours, oracle) >= 60 dB and |SI-SDR vs clean difference| <= 0.05 dB.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -358,9 +361,9 @@ def test_full_size_properties_config2(dev):
 
 # ---------------------------------------------------------------------------------------------- fast vs generic kernels
 @pytest.mark.parametrize("n_fft,hop", [(1024, 512), (512, 256), (2048, 1024)])
-def test_fast_kernels_match_generic_kernels(dev, monkeypatch, n_fft, hop):
-    """n_fft 1024 and 512 have register/TMA fast kernels (gl_fast.cu, gl_fast_n512.cu); the generic shared-memory kernels
-    are the cross-check.  Same C-ABI calls, same seed for the in-kernel rand_init draws."""
+def test_fast_kernels_match_generic_kernels(dev, n_fft, hop):
+    """n_fft 1024 / 512 / 2048 have register/TMA fast kernels (gl_fast*.cu); the generic shared-memory kernels (plan flag
+    B2D_PLAN_GENERIC_KERNELS) are the cross-check.  Same C-ABI calls, same seed for the in-kernel rand_init draws."""
     import audio_denoising_b200 as adb
     from audio_denoising_b200 import _cabi, _runtime
 
@@ -368,27 +371,26 @@ def test_fast_kernels_match_generic_kernels(dev, monkeypatch, n_fft, hop):
     B, L = 5, 20000
     x, _ = synth.make_batch(B, L, 16000, start=90)
     xd = x.to(dev)
-    plan = _runtime.get_plan(n_fft, hop, 64, 16000, dev)
-    T = plan.num_frames(L)
+    plan_fast = _runtime.get_plan(n_fft, hop, 64, 16000, dev)
+    plan_generic = _runtime.get_plan(n_fft, hop, 64, 16000, dev, flags=_runtime.PLAN_GENERIC_KERNELS)
+    T = plan_fast.num_frames(L)
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
 
-    def logmel():
+    def logmel(plan):
         out = torch.empty(B, T, 64, device=dev)
         _cabi.check(lib.b2d_stft_mel_log1p(plan.handle, xd.data_ptr(), None, B, L, out.data_ptr(), None, None, st))
         return out.cpu()
 
-    def gl(seed, n_iter):
+    def gl(plan, seed, n_iter):
         mag = dsp.stft(x, n_fft, hop).abs().to(dev)
         ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(plan.handle, B, T), dtype=torch.uint8, device=dev)
         wave = torch.empty(B, plan.out_length(T), device=dev)
         _cabi.check(lib.b2d_griffinlim(plan.handle, mag.data_ptr(), None, seed, B, T, n_iter, 0.99, None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
         return wave.cpu()
 
-    fast = dict(logmel=logmel(), gl0=gl(77, 0), gl4=gl(77, 4), gl32=gl(77, 32), ones=gl(0, 8))
-    monkeypatch.setenv("B2D_GL_GENERIC", "1")
-    monkeypatch.setenv("B2D_STFT_GENERIC", "1")
-    slow = dict(logmel=logmel(), gl0=gl(77, 0), gl4=gl(77, 4), gl32=gl(77, 32), ones=gl(0, 8))
+    fast, slow = (dict(logmel=logmel(pl), gl0=gl(pl, 77, 0), gl4=gl(pl, 77, 4), gl32=gl(pl, 77, 32), ones=gl(pl, 0, 8))
+                  for pl in (plan_fast, plan_generic))
     assert metrics.rel_l2(fast["logmel"], slow["logmel"]) < 2e-6
     assert metrics.rel_l2(fast["logmel"], dsp.log_mel(x, n_fft, hop, dsp.mel_fbanks(n_fft // 2 + 1, 64, 16000)).transpose(1, 2)) < 5e-6
     assert metrics.si_sdr(fast["gl0"], slow["gl0"]).min() > 110.0  # same random initial phase from the same seed
@@ -408,8 +410,7 @@ def test_fast_kernels_match_generic_kernels(dev, monkeypatch, n_fft, hop):
     assert metrics.si_sdr(fast["ones"], slow["ones"]).min() > 90.0
     assert metrics.si_sdr(fast["ones"], dsp.griffinlim(dsp.stft(x, n_fft, hop).abs(), n_fft, hop, 8, 0.99, None, rand_init=False)).min() > 80.0
     # a different seed gives a different (but equally consistent) reconstruction
-    monkeypatch.delenv("B2D_GL_GENERIC")
-    other = gl(78, 32)
+    other = gl(plan_fast, 78, 32)
     assert metrics.si_sdr(other, fast["gl32"]).max() < 30.0
     mag = dsp.stft(x, n_fft, hop).abs()
     assert metrics.rel_l2(dsp.stft(other, n_fft, hop).abs(), mag) < 0.35
@@ -676,31 +677,27 @@ def test_denoise_host_pcm16_matches_float_path(dev):
 
 
 @pytest.mark.parametrize("n_fft", [512, 1024, 2048, 640, 1536])
-def test_fast_paths_match_generic_on_ragged_shapes(dev, monkeypatch, n_fft):
+def test_fast_paths_match_generic_on_ragged_shapes(dev, n_fft):
     """Run partitions of every flavour (single short run, odd run lengths, a last run of one frame, more runs than warp
-    slots) for the three register fast paths: 3 iterations from all-ones angles against the generic kernel."""
+    slots) for the register fast paths: 3 iterations from all-ones angles against the generic kernel."""
     from audio_denoising_b200 import _cabi, _runtime
 
     _, metrics, *_ = _oracle()
     hop = n_fft // 2
-    plan = _runtime.get_plan(n_fft, hop, 0, 0, dev)
+    plans = [_runtime.get_plan(n_fft, hop, 0, 0, dev), _runtime.get_plan(n_fft, hop, 0, 0, dev, flags=_runtime.PLAN_GENERIC_KERNELS)]
+    plan = plans[0]
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     g = torch.Generator().manual_seed(n_fft)
     for B, T in [(1, 3), (1, 4), (2, 5), (3, 7), (1, 33), (5, 18), (2, 126), (700, 9), (37, 23)]:
         mag = (torch.rand(B, T, plan.frame_stride, generator=g) * 2).to(dev)
-        ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(plan.handle, B, T), dtype=torch.uint8, device=dev)
         outs = []
-        for generic in (False, True):
-            if generic:
-                monkeypatch.setenv("B2D_GL_GENERIC", "1")
-            else:
-                monkeypatch.delenv("B2D_GL_GENERIC", raising=False)
-            wave = torch.zeros(B, plan.out_length(T), device=dev)
-            _cabi.check(lib.b2d_griffinlim_frames(plan.handle, mag.data_ptr(), None, 0, B, T, 3, 0.99, None, wave.data_ptr(),
+        for pl in plans:
+            ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(pl.handle, B, T), dtype=torch.uint8, device=dev)
+            wave = torch.zeros(B, pl.out_length(T), device=dev)
+            _cabi.check(lib.b2d_griffinlim_frames(pl.handle, mag.data_ptr(), None, 0, B, T, 3, 0.99, None, wave.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), st))
             outs.append(wave.cpu())
-        monkeypatch.delenv("B2D_GL_GENERIC", raising=False)
         assert torch.isfinite(outs[0]).all()
         sdr = metrics.si_sdr(outs[0], outs[1])
         # random magnitudes are not a consistent spectrogram: where a rebuilt value nearly cancels, the unit-modulus projection
@@ -751,7 +748,8 @@ def test_denoise_pcm16_native_call_equals_float_chain(dev):
         init = synth.gl_init_angles((B, 513, T), seed=5).to(dev)
         pcm = (noisy * 0.8 * 32767).to(torch.int16).to(dev)
         got, hx1 = pipe.denoise_pcm16(pcm, init_angles=init)
-        wave, hx2 = pipe.denoise(pcm.float() / 32767, init_angles=init)
+        xf = torch.from_numpy(pcm.cpu().numpy().astype(np.float32) / np.float32(32767)).to(dev)  # true division (torch CUDA multiplies by 1/s)
+        wave, hx2 = pipe.denoise(xf, init_angles=init)
         want = (wave.clamp(-1, 1) * 32767).to(torch.int16)
         assert got.dtype == torch.int16 and got.shape == want.shape
         assert torch.equal(got, want)
@@ -853,3 +851,52 @@ def test_streaming_graph_follows_weight_changes(dev):
         m.cell.input_gate.downs[0].conv.bias.data.add_(0.5)
     m.repack()
     assert m.native_model(dev) is not h0
+
+
+def test_exact_math_attribution(dev, golden):
+    """where do the dB between the GPU path and the CPU oracle / reference goldens go?  Runs the chain with
+    every approximation swapped for the exact operation, one switch at a time (plan flags B2D_PLAN_EXACT_*, conv_mode fp32,
+    B2D_CONV_EXACT_GATES), and all together.  The table is printed (and written to gpurun_out/ when that directory exists);
+    the asserts keep the default path at the agreed bar and make sure no switch makes things worse by more than noise."""
+    import audio_denoising_b200 as adb
+    from audio_denoising_b200 import _runtime as rt
+
+    dsp, metrics, model, pipeline, synth = _oracle()
+    m, sd, cfg = _our_model("good", dev)
+    cases = []
+    # the smoke() case: 2 clips of 1 s, oracle run here with the same injected initial phase
+    noisy, _ = synth.make_batch(2, 16000, 16000)
+    T = 1 + 16000 // 512
+    init = synth.gl_init_angles((2, 513, T), seed=7)
+    ref = pipeline.denoise_batch(noisy, model.GRUUNet2Oracle(sd, cfg), 1024, 512, 64, 16000, 32, 0.99, init)["wave"]
+    cases.append(("smoke", 1024, 512, 16000, noisy, init, ref, True))
+    c = golden("dsp_chain.npz")
+    for tag in ("a", "b", "c"):
+        n_fft, hop, sr, L = [int(v) for v in c[f"{tag}_cfg"]]
+        cases.append((f"golden_{tag}", n_fft, hop, sr, torch.from_numpy(c[f"{tag}_noisy"]), torch.from_numpy(c[f"{tag}_init"]),
+                      torch.from_numpy(c[f"{tag}_wave"]), False))
+    switches = [("default", 0, "mma", False), ("exact_sqrt", rt.PLAN_EXACT_SQRT, "mma", False), ("exact_unit", rt.PLAN_EXACT_UNIT, "mma", False),
+                ("exact_peak_div", rt.PLAN_EXACT_PEAK_DIV, "mma", False), ("fp32_invmel", rt.PLAN_FP32_INVMEL, "mma", False),
+                ("fp32_conv", 0, "fp32", False), ("exact_gates", 0, "mma", True), ("all_exact", rt.PLAN_EXACT_ALL, "fp32", True),
+                ("generic_kernels", rt.PLAN_GENERIC_KERNELS, "mma", False)]
+    table = {}
+    for name, n_fft, hop, sr, x, ini, want, norm in cases:
+        row = {}
+        for sw, flags, conv, gates in switches:
+            m.conv_mode, m.exact_gates = conv, gates
+            pipe = adb.DenoisePipeline(m, n_fft=n_fft, hop_length=hop, n_mels=64, sample_rate=sr, n_iter=32, plan_flags=flags)
+            wave, _ = pipe.denoise(x.to(dev), init_angles=ini.to(dev), normalise=norm)
+            row[sw] = [round(float(v), 1) for v in metrics.si_sdr(wave.cpu(), want)]
+        table[name] = row
+    m.conv_mode, m.exact_gates = "mma", False
+    print("\nSI-SDR(ours, oracle / reference golden) in dB per exact-math switch:")
+    for name, row in table.items():
+        for sw, v in row.items():
+            print(f"  {name:10s} {sw:16s} {v}")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "exact_math_attribution.json"), "w") as f:
+            json.dump(table, f, indent=1)
+    for name, row in table.items():
+        assert min(row["default"]) >= 40.0, (name, row["default"])
+        assert min(row["all_exact"]) >= 40.0, (name, row["all_exact"])
