@@ -38,17 +38,17 @@ extern std::atomic<unsigned long long> g_launches;
       return ::b2d::fail(B2D_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
-// Opt a kernel in to the full 227 KB of dynamic shared memory once per device (the attribute belongs to the function, not
-// to the launch): every launch site states its kernel here instead of calling cudaFuncSetAttribute per launch.
-#define B2D_SMEM_OPT_IN(...)                                                                                     \
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the function (per device), not to the
+// launch, so it is set when a launch site first needs more than it has asked for before -- not on every launch.
+#define B2D_SMEM_OPT_IN(bytes, ...)                                                                              \
   do {                                                                                                           \
-    static std::atomic<unsigned long long> seen__{0};                                                            \
+    static std::atomic<int> have__[16];                                                                          \
     int dev__ = 0;                                                                                               \
     cudaGetDevice(&dev__);                                                                                       \
-    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                       \
-    if (!(seen__.load(std::memory_order_acquire) & bit__)) {                                                     \
-      B2D_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));          \
-      seen__.fetch_or(bit__, std::memory_order_release);                                                         \
+    const int want__ = (int)(bytes);                                                                             \
+    if (have__[dev__ & 15].load(std::memory_order_acquire) < want__) {                                           \
+      B2D_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, want__));          \
+      have__[dev__ & 15].store(want__, std::memory_order_release);                                               \
     }                                                                                                            \
   } while (0)
 

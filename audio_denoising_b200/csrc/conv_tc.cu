@@ -391,7 +391,7 @@ int model_pack_tc(b2d_model* m) { (void)m; return B2D_OK; }  // weights are pack
 template <int NP, int KP>
 static int launch_layer(const TcLayer& L, int num_sms, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)(2 * 128 * KP + 2 * NP * KP) + 64;
-  B2D_SMEM_OPT_IN(conv_tc_kernel<NP, KP>);
+  B2D_SMEM_OPT_IN(smem, conv_tc_kernel<NP, KP>);
   const int fpt = 128 / L.lout;
   const size_t tiles = (L.nframes + fpt - 1) / fpt;
   const size_t cap = (size_t)num_sms * (smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3));
@@ -474,7 +474,7 @@ int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes
   TcInvMel L;
   L.mel = mel_bt; L.wimg = reinterpret_cast<const float*>(p->d_tw8); L.out = mag_tf; L.nframes = nframes; L.Fp = p->Fp; L.terms = terms;
   const size_t smem = sizeof(float) * (size_t)(2 * 128 * IM_K + 2 * IM_N * IM_K) + 64;
-  B2D_SMEM_OPT_IN(invmel_tc_kernel);
+  B2D_SMEM_OPT_IN(smem, invmel_tc_kernel);
   const size_t tiles = (nframes + 127) / 128;
   const int ncols = (p->Fp + IM_N - 1) / IM_N;
   const size_t cap = (size_t)(p->num_sms / ncols > 0 ? p->num_sms / ncols : 1);

@@ -451,16 +451,16 @@ int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, in
   // a streaming hop is a single CTA per session: give it more threads; batches keep 256 (several CTAs per SM)
   const int threads = ((long)grid.x * grid.y <= 2 * p->num_sms) ? 512 : 256;
   if (p->M == 320) {
-    B2D_SMEM_OPT_IN(stft_kernel<320>);
+    B2D_SMEM_OPT_IN(smem, stft_kernel<320>);
     stft_kernel<320><<<grid, threads, smem, st>>>(a);
   } else if (p->M == 512) {
-    B2D_SMEM_OPT_IN(stft_kernel<512>);
+    B2D_SMEM_OPT_IN(smem, stft_kernel<512>);
     stft_kernel<512><<<grid, threads, smem, st>>>(a);
   } else if (p->M == 768) {
-    B2D_SMEM_OPT_IN(stft_kernel<768>);
+    B2D_SMEM_OPT_IN(smem, stft_kernel<768>);
     stft_kernel<768><<<grid, threads, smem, st>>>(a);
   } else {
-    B2D_SMEM_OPT_IN(stft_kernel<0>);
+    B2D_SMEM_OPT_IN(smem, stft_kernel<0>);
     stft_kernel<0><<<grid, threads, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("stft_kernel");
@@ -485,11 +485,11 @@ int launch_inverse_mel(const b2d_plan* p, const float* mel, int B, int T, float*
   const int K = p->n_mels;
   const size_t smem = sizeof(float) * 2 * K * 68;
   if (torch_layout) {
-    B2D_SMEM_OPT_IN(inverse_mel_kernel<true>);
+    B2D_SMEM_OPT_IN(smem, inverse_mel_kernel<true>);
     dim3 grid((p->F + 63) / 64, (T + 63) / 64, B);
     inverse_mel_kernel<true><<<grid, 256, smem, st>>>(mel, p->d_pinv, out, B, T, K, p->F, p->Fp);
   } else {
-    B2D_SMEM_OPT_IN(inverse_mel_kernel<false>);
+    B2D_SMEM_OPT_IN(smem, inverse_mel_kernel<false>);
     const size_t NF = (size_t)B * T;
     dim3 grid((p->Fp + 63) / 64, (unsigned)((NF + 63) / 64), 1);
     inverse_mel_kernel<false><<<grid, 256, smem, st>>>(mel, p->d_pinv, out, B, T, K, p->F, p->Fp);
@@ -505,7 +505,7 @@ int launch_istft(const b2d_plan* p, const float2* spec, const float* mag, int B,
   a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.fd = p->fft;
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.winn = p->d_winn; a.inv_env = p->d_inv_env; a.wave = wave;
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * a.G * p->M) + 16;
-  B2D_SMEM_OPT_IN(istft_kernel);
+  B2D_SMEM_OPT_IN(smem, istft_kernel);
   dim3 grid((T - 1 + a.G - 2) / (a.G - 1), B);
   istft_kernel<<<grid, 256, smem, st>>>(a);
   B2D_LAUNCH_CHECK("istft_kernel");

@@ -63,6 +63,11 @@ constexpr int IT_OFF_RING = IT_OFF_BAR + 16;
 constexpr int IT_OFF_XBAR = IT_OFF_RING + 2 * 2 * HOP * 4;
 constexpr int IT_WARP_SMEM = IT_OFF_XBAR + 16;                  // 14912 B
 constexpr int IT_WARPS = 12;                                    // one persistent 12-warp CTA per SM (168 registers / thread)
+// (Measured, round 2: with `tprev` gone the kernel no longer waits on HBM -- DRAM traffic fell from 436 MB to ~290 MB per
+//  launch for 89.3 -> 86.9 us -- it is bound by the shared-memory pipe and issue slots.  Reading the 21 lane twiddles from
+//  CTA-wide shared-memory tables instead of 42 registers fits 128 registers and 14 warps per SM, and is SLOWER: 94.8 us at
+//  12 warps, 96.9 at 13, 91.9 at 14 (B = 256; 281 -> 306 us at B = 1024): +42 LDS.64 per frame cost more than two more
+//  warps give.  tools/tune_gl.py history, gpurun r2.)
 
 // normalised (not yet windowed) sample `is` of interior hop-block js of clip b: the sum of the two partial slots on a run boundary
 __device__ __forceinline__ float partial_sample(const float* __restrict__ part, int b, int R, int n, int js, int is) {
@@ -399,7 +404,7 @@ int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, 
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
   constexpr int W = 8;
   const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
-  B2D_SMEM_OPT_IN(gl_fast512_init_kernel<W>);
+  B2D_SMEM_OPT_IN(smem, gl_fast512_init_kernel<W>);
   gl_fast512_init_kernel<W><<<(B * R + W - 1) / W, W * 32, smem, st>>>(a);
   B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
   return B2D_OK;
@@ -585,7 +590,7 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   constexpr int W = STFT_WARPS;
   B2D_REQUIRE(p->mel_seg_pad <= 320, B2D_ERR_UNSUPPORTED, "mel filterbank too dense for the n_fft = 1024 fast kernel");
   const size_t smem = sizeof(float2) * 1024 + (size_t)p->mel_seg_pad * 36 + sizeof(int) * ((p->n_mels + 4) & ~3) + (size_t)W * STFT_WSMEM;
-  B2D_SMEM_OPT_IN(stft_fast512_kernel);
+  B2D_SMEM_OPT_IN(smem, stft_fast512_kernel);
   const size_t nframes = (size_t)B * a.T;
   const size_t want = (nframes + W - 1) / W;
   const int grid = (int)(want < (size_t)p->num_sms ? want : (size_t)p->num_sms);
@@ -598,16 +603,16 @@ int gl_fast_warps_per_sm() { return IT_WARPS; }
 
 template <bool USE_PREV, bool EXACT>
 static int launch_iteration(const GlFastArgs& a, int num_sms, cudaStream_t st) {
-  static bool configured = false;  // per instantiation; the attribute is a property of the function, set once per process
   const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)IT_WARPS * IT_WARP_SMEM;
-  if (!configured) {
-    B2D_SMEM_OPT_IN(gl_fast512_kernel<USE_PREV, EXACT>);
-    configured = true;
-  }
+  B2D_SMEM_OPT_IN(smem, gl_fast512_kernel<USE_PREV, EXACT>);
   const int runs = a.B * a.R;
   gl_fast512_kernel<USE_PREV, EXACT><<<runs < num_sms ? runs : num_sms, IT_WARPS * 32, smem, st>>>(a);
   B2D_LAUNCH_CHECK("gl_fast512_kernel");
   return B2D_OK;
+}
+template <bool EXACT>
+static int launch_iteration_p(const GlFastArgs& a, int use_prev, int num_sms, cudaStream_t st) {
+  return use_prev ? launch_iteration<true, EXACT>(a, num_sms, st) : launch_iteration<false, EXACT>(a, num_sms, st);
 }
 
 int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, const float* xin, const float* xprev, float* xout, int B, int T,
@@ -618,8 +623,8 @@ int launch_gl_fast512(const b2d_plan* p, const float* mag_tf, const float* xin, 
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
   a.mom = mom; a.wave = wave; a.out_scale = out_scale;
   const bool exact = (p->flags & B2D_PLAN_EXACT_UNIT) != 0;
-  if (use_prev) return exact ? launch_iteration<true, true>(a, p->num_sms, st) : launch_iteration<true, false>(a, p->num_sms, st);
-  return exact ? launch_iteration<false, true>(a, p->num_sms, st) : launch_iteration<false, false>(a, p->num_sms, st);
+  if (exact) return launch_iteration_p<true>(a, use_prev, p->num_sms, st);
+  return launch_iteration_p<false>(a, use_prev, p->num_sms, st);
 }
 
 }  // namespace b2d

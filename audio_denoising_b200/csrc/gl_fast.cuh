@@ -32,8 +32,10 @@ struct LaneTw {
   float2 a[8];   // W512^{p k1}
   float2 b[8];   // W512^{(p+32) k1}
   float2 c[8];   // W64^{(p&7) k2}
+  B2D_HD float2 A(int k) const { return a[k]; }
+  B2D_HD float2 Bq(int k) const { return b[k]; }
+  B2D_HD float2 Cq(int k) const { return c[k]; }
 };
-
 B2D_HD void lane_twiddles(int lane, const float2* __restrict__ tw512, LaneTw& t) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -60,12 +62,13 @@ B2D_HD void bfly8x2(float2* r) {
 B2D_HD int fam(int lane, int f) { return f == 0 ? lane : (lane == 0 ? 32 : 64 - lane); }
 
 // ---- forward ------------------------------------------------------------------------------------
-B2D_HD void fwd1_store(int lane, float2* v, const LaneTw& t, float2* S) {
+template <typename TW>
+B2D_HD void fwd1_store(int lane, float2* v, const TW& t, float2* S) {
   bfly8x2<false>(v);
 #pragma unroll
   for (int k1 = 0; k1 < 8; ++k1) {
     float2 a = v[2 * k1], b = v[2 * k1 + 1];
-    if (k1) { a = cmul(a, t.a[k1]); b = cmul(b, t.b[k1]); }
+    if (k1) { a = cmul(a, t.A(k1)); b = cmul(b, t.Bq(k1)); }
     S[k1 * LD1 + lane] = a;
     S[k1 * LD1 + lane + 32] = b;
   }
@@ -78,13 +81,14 @@ B2D_HD void fwd2_load(int lane, float2* u, const float2* S) {
     u[2 * n2 + 1] = S[(kq + 4) * LD1 + 8 * n2 + n3];
   }
 }
-B2D_HD void fwd2_store(int lane, float2* u, const LaneTw& t, float2* S) {
+template <typename TW>
+B2D_HD void fwd2_store(int lane, float2* u, const TW& t, float2* S) {
   const int kq = lane >> 3, n3 = lane & 7;
   bfly8x2<false>(u);
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
     float2 a = u[2 * k2], b = u[2 * k2 + 1];
-    if (k2) { a = cmul(a, t.c[k2]); b = cmul(b, t.c[k2]); }
+    if (k2) { const float2 c = t.Cq(k2); a = cmul(a, c); b = cmul(b, c); }
     S[n3 * LD2 + kq + 8 * k2] = a;
     S[n3 * LD2 + kq + 4 + 8 * k2] = b;
   }
@@ -109,12 +113,13 @@ B2D_HD void inv1_store(int lane, float2* w, float2* S) {
     S[n3 * LD2 + j1] = w[2 * n3 + 1];
   }
 }
-B2D_HD void inv2_load(int lane, float2* u, const LaneTw& t, const float2* S) {
+template <typename TW>
+B2D_HD void inv2_load(int lane, float2* u, const TW& t, const float2* S) {
   const int kq = lane >> 3, n3 = lane & 7;
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
     float2 a = S[n3 * LD2 + kq + 8 * k2], b = S[n3 * LD2 + kq + 4 + 8 * k2];
-    if (k2) { a = cmulc(a, t.c[k2]); b = cmulc(b, t.c[k2]); }
+    if (k2) { const float2 c = t.Cq(k2); a = cmulc(a, c); b = cmulc(b, c); }
     u[2 * k2] = a;
     u[2 * k2 + 1] = b;
   }
@@ -128,11 +133,12 @@ B2D_HD void inv2_store(int lane, const float2* u, float2* S) {
     S[(kq + 4) * LD1 + 8 * n2 + n3] = u[2 * n2 + 1];
   }
 }
-B2D_HD void inv3_load(int lane, float2* v, const LaneTw& t, const float2* S) {
+template <typename TW>
+B2D_HD void inv3_load(int lane, float2* v, const TW& t, const float2* S) {
 #pragma unroll
   for (int k1 = 0; k1 < 8; ++k1) {
     float2 a = S[k1 * LD1 + lane], b = S[k1 * LD1 + lane + 32];
-    if (k1) { a = cmulc(a, t.a[k1]); b = cmulc(b, t.b[k1]); }
+    if (k1) { a = cmulc(a, t.A(k1)); b = cmulc(b, t.Bq(k1)); }
     v[2 * k1] = a;
     v[2 * k1 + 1] = b;
   }

@@ -330,7 +330,7 @@ template <bool USE_PREV, bool INIT>
 static int launch_n2048(const GlN2048Args& a, int grid, cudaStream_t st) {
   using namespace n2048;
   const size_t smem = TABLE_BYTES + (size_t)PAIRS * PSMEM;
-  B2D_SMEM_OPT_IN(gl_fast_n2048_kernel<USE_PREV, INIT>);
+  B2D_SMEM_OPT_IN(smem, gl_fast_n2048_kernel<USE_PREV, INIT>);
   gl_fast_n2048_kernel<USE_PREV, INIT><<<grid, PAIRS * 64, smem, st>>>(a);
   B2D_LAUNCH_CHECK("gl_fast_n2048_kernel");
   return B2D_OK;

@@ -271,10 +271,10 @@ int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, c
   const int runs = B * R;
   const int grid = runs < p->num_sms ? runs : p->num_sms;
   if (use_prev) {
-    B2D_SMEM_OPT_IN(gl_fast_n512_kernel<true>);
+    B2D_SMEM_OPT_IN(smem, gl_fast_n512_kernel<true>);
     gl_fast_n512_kernel<true><<<grid, WARPS * 32, smem, st>>>(a);
   } else {
-    B2D_SMEM_OPT_IN(gl_fast_n512_kernel<false>);
+    B2D_SMEM_OPT_IN(smem, gl_fast_n512_kernel<false>);
     gl_fast_n512_kernel<false><<<grid, WARPS * 32, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("gl_fast_n512_kernel");

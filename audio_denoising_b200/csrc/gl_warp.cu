@@ -267,10 +267,10 @@ int launch_gl_warp(const b2d_plan* p, const float* mag_tf, float2* tprev, const 
   const int runs = B * R;
   const int grid = runs < p->num_sms ? runs : p->num_sms;
   if (use_prev) {
-    B2D_SMEM_OPT_IN(gl_warp_kernel<true>);
+    B2D_SMEM_OPT_IN(smem, gl_warp_kernel<true>);
     gl_warp_kernel<true><<<grid, a.warps * 32, smem, st>>>(a);
   } else {
-    B2D_SMEM_OPT_IN(gl_warp_kernel<false>);
+    B2D_SMEM_OPT_IN(smem, gl_warp_kernel<false>);
     gl_warp_kernel<false><<<grid, a.warps * 32, smem, st>>>(a);
   }
   B2D_LAUNCH_CHECK("gl_warp_kernel");

@@ -386,10 +386,10 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     // fused mode: one CTA walks all the steps of a short clip alone, give it the whole SM (measured per-hop latency, n_fft 640 /
     // 1536: 0.222 / 0.579 ms with 256 threads, 0.207 / 0.371 with 512, 0.211 / 0.357 with 1024)
     if (args.fused_iters >= 0) threads = p->M >= 640 ? 1024 : (p->M >= 256 ? 512 : 256);
-    if (mt == 320) { B2D_SMEM_OPT_IN(gl_generic_kernel<320>); gl_generic_kernel<320><<<g, threads, smem, st>>>(args); }
-    else if (mt == 768) { B2D_SMEM_OPT_IN(gl_generic_kernel<768>); gl_generic_kernel<768><<<g, threads, smem, st>>>(args); }
-    else if (mt == 512) { B2D_SMEM_OPT_IN(gl_generic_kernel<512>); gl_generic_kernel<512><<<g, threads, smem, st>>>(args); }
-    else { B2D_SMEM_OPT_IN(gl_generic_kernel<0>); gl_generic_kernel<0><<<g, threads, smem, st>>>(args); }
+    if (mt == 320) { B2D_SMEM_OPT_IN(smem, gl_generic_kernel<320>); gl_generic_kernel<320><<<g, threads, smem, st>>>(args); }
+    else if (mt == 768) { B2D_SMEM_OPT_IN(smem, gl_generic_kernel<768>); gl_generic_kernel<768><<<g, threads, smem, st>>>(args); }
+    else if (mt == 512) { B2D_SMEM_OPT_IN(smem, gl_generic_kernel<512>); gl_generic_kernel<512><<<g, threads, smem, st>>>(args); }
+    else { B2D_SMEM_OPT_IN(smem, gl_generic_kernel<0>); gl_generic_kernel<0><<<g, threads, smem, st>>>(args); }
     return B2D_OK;
   };
   dim3 grid(q.R, B);

@@ -542,10 +542,10 @@ int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* 
   const int grid = (int)(want < (size_t)num_sms ? want : (size_t)num_sms);
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma) + (size_t)dfrag_off(4) * 32;
   if (terms == 3) {
-    B2D_SMEM_OPT_IN(encoder_mma_kernel<3>);
+    B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<3>);
     encoder_mma_kernel<3><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
   } else {
-    B2D_SMEM_OPT_IN(encoder_mma_kernel<1>);
+    B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<1>);
     encoder_mma_kernel<1><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
   }
   B2D_LAUNCH_CHECK("encoder_mma_kernel");
@@ -561,10 +561,10 @@ int model_decode_mma(const b2d_model* m, const float* hseq, const float* d0, con
   const int grid = (int)(want < (size_t)num_sms ? want : (size_t)num_sms);
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma);
   if (terms == 3) {
-    B2D_SMEM_OPT_IN(decoder_mma_kernel<3>);
+    B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<3>);
     decoder_mma_kernel<3><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
   } else {
-    B2D_SMEM_OPT_IN(decoder_mma_kernel<1>);
+    B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<1>);
     decoder_mma_kernel<1><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
   }
   B2D_LAUNCH_CHECK("decoder_mma_kernel");
