@@ -434,11 +434,18 @@ int launch_pcm16_ingest_peak(const short* pcm, int B, int L, float* wave, float*
 int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                         cudaStream_t st);  // gl_fast.cu
 
+bool stft_reg_supported(const b2d_plan* p, int B, int L);  // gl_reg.cu
+int launch_stft_reg(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt, cudaStream_t st);
+
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
                 float* logmel_bm, float2* spec, cudaStream_t st) {
   if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 && p->mel_seg_pad <= 320 && (long long)B * (1 + L / p->hop) < (1ll << 30) &&
       !(p->flags & B2D_PLAN_GENERIC_KERNELS))
     return launch_stft_fast512(p, wave, inv_scale, B, L, logmel_bt, st);
+  // n_fft 640 / 1536 batches: register-FFT kernel (a single streaming hop -- 3 frames per session -- stays on the block kernel)
+  if (logmel_bt && !logmel_bm && !spec && !(p->flags & B2D_PLAN_GENERIC_KERNELS) && stft_reg_supported(p, B, L) &&
+      (long long)B * (1 + L / p->hop) >= 64)
+    return launch_stft_reg(p, wave, inv_scale, B, L, logmel_bt, st);
   StftArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.G = frames_per_block(p);
   a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.n_mels = p->n_mels; a.fd = p->fft;

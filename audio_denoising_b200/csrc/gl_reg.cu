@@ -1,0 +1,535 @@
+// gl_reg.cu -- Griffin-Lim iteration and fused STFT + Mel for n_fft = 128 * R3 with a register-resident FFT (gl_reg.cuh):
+// n_fft 640 (R3 = 5: the 20 ms hop of BASELINE config 3 in batch mode) and n_fft 1536 (R3 = 12: the reference app's own
+// 48 kHz geometry, app3.py:29-33).  Same structure as the n_fft = 1024 kernel (gl_fast.cu): one warp owns a frame, walks a
+// run of frames with the overlap-add carry in registers, the momentum term is formed on the time-domain iterates
+// (d = x_k - m x_{k-1}, see gl_fast.cu), the mag row and the hop-blocks of both iterates arrive by TMA one frame ahead, one
+// persistent CTA per SM.  Round 1 ran these lengths on shared-memory Stockham kernels at 19 % / 25 % of HBM peak.
+#include "gl_reg.cuh"
+#include "kernels.cuh"
+#include "tma.cuh"
+
+namespace b2d {
+
+using namespace regfft;
+
+struct GlRegArgs {
+  const float* mag_tf;   // [B,T,Fp]
+  const float* xin;      // x_k, partial hop-block format
+  const float* xprev;    // x_{k-1} (read only when USE_PREV)
+  float* xout;           // x_{k+1}
+  int B, T, n, R, Fp;
+  const float2* tw;      // W_M^k
+  const float2* rtw;     // W_N^k, k < M
+  const float* win;      // [N]
+  const float* winn;     // [N] win / N
+  const float* inv_env;  // [HOP]
+  float mom;
+  float* wave;             // last iteration: [B, HOP*(T-1)] or null
+  const float* out_scale;  // [B] or null
+  unsigned long long seed;             // MODE_INIT: 0 = all-ones angles, else in-kernel counter-based U[0,1)^2 draws
+  const unsigned long long* seed_ptr;  // optional device-resident seed
+};
+// kernel modes: one iteration without / with the momentum term, or x_0 = istft(mag * angles_0) (the inverse half only)
+constexpr int MODE_FIRST = 0, MODE_ITER = 1, MODE_INIT = 2;
+
+template <int R3>
+struct RegSmem {
+  typedef Geo<R3> G;
+  static constexpr int MAG_BYTES = (G::M + 4) * 4;                       // Fp floats, a multiple of 16
+  static constexpr int OFF_MAG = G::XCH * 8;
+  static constexpr int OFF_BAR = OFF_MAG + ((MAG_BYTES + 15) & ~15);
+  static constexpr int OFF_RING = OFF_BAR + 16;
+  static constexpr int OFF_XBAR = OFF_RING + 2 * 2 * G::HOP * 4;         // two slots x [x_k block | x_{k-1} block]
+  static constexpr int WARP_BYTES = OFF_XBAR + 16;
+  static constexpr int TABLE_BYTES = (G::M / 2 + G::M / 2 + G::M + G::M) * 8;  // WA | WB | WN | RT (float2)
+};
+
+// sample `is` of interior hop-block js of clip b in the partial format: the sum of two slots on a run boundary
+template <int HOP>
+__device__ __forceinline__ float reg_partial_sample(const float* __restrict__ part, int b, int R, int n, int js, int is) {
+  const int r1 = (js - 1) / n, r2 = js / n;
+  float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
+  if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
+  return v;
+}
+template <int HOP>
+__device__ __noinline__ void reg_stage_reflect(const float* __restrict__ part, const float* __restrict__ prev, float mom,
+                                               const float* __restrict__ inv_env, const float* __restrict__ win_half, int b, int R,
+                                               int n, int T, int j, float* __restrict__ dst, int lane) {
+  for (int i = lane; i < HOP; i += 32) {
+    int js, is;
+    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
+    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
+    float v = reg_partial_sample<HOP>(part, b, R, n, js, is);
+    if (prev) v = fmaf(-mom, reg_partial_sample<HOP>(prev, b, R, n, js, is), v);
+    dst[i] = v * inv_env[is] * win_half[i];
+  }
+}
+
+template <int R3, int WARPS, int MODE>
+__global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_kernel(const GlRegArgs a) {
+  constexpr bool USE_PREV = (MODE == MODE_ITER);
+  constexpr bool INIT = (MODE == MODE_INIT);
+  typedef Geo<R3> G;
+  typedef RegSmem<R3> SM;
+  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2;  // H2: float2 per hop-block
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WA = reinterpret_cast<float2*>(smem_raw);  // inv_env * win, first half   [H2]
+  float2* WB = WA + H2;                              // inv_env * win, second half  [H2]
+  float2* WN = WB + H2;                              // win / N                     [M]
+  float2* RT = WN + M;                               // W_N^k                       [M]
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + M);
+  for (int i = threadIdx.x; i < H2; i += blockDim.x) {
+    WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
+    WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = a.n, R = a.R, T = a.T;
+  const int nruns = a.B * a.R;
+  const int gw0 = warp * (int)gridDim.x + (int)blockIdx.x;  // runs dealt round-robin over the CTAs
+  const int gstep = WARPS * (int)gridDim.x;
+  if (gw0 >= nruns) return;
+  unsigned char* wsm = warp_base + (size_t)warp * SM::WARP_BYTES;
+  float2* S = reinterpret_cast<float2*>(wsm);
+  float* mg_s = reinterpret_cast<float*>(wsm + SM::OFF_MAG);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + SM::OFF_BAR);
+  float* xs = reinterpret_cast<float*>(wsm + SM::OFF_RING);  // slot s: x_k block at xs + s * 2 * HOP, x_{k-1} block behind it
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(wsm + SM::OFF_XBAR);
+  if (lane == 0) {
+    tma::barrier_init(bar, 1);
+    tma::barrier_init(xbar, 1);
+    tma::barrier_init(xbar + 1, 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+  LaneTwR<R3> tw;
+  lane_twiddles_r<R3>(lane, a.tw, tw);
+  const size_t run_stride = (size_t)(n + 1) * HOP;
+  const float2 nmom = make_float2(-a.mom, -a.mom);
+  constexpr uint32_t ring_bytes = (USE_PREV ? 2u : 1u) * HOP * 4u;
+  uint32_t tma_uses = 0, xuse0 = 0, xuse1 = 0;
+
+#pragma unroll 1
+  for (int gw = gw0; gw < nruns; gw += gstep) {
+    const int b = gw / R, r = gw - b * R;
+    const int tb = r * n, te = min(T, tb + n);
+    const float* xrun = a.xin + (size_t)(b * R + r) * run_stride;
+    const float* prun = a.xprev + (size_t)(b * R + r) * run_stride;
+    float* xo = a.xout + (size_t)(b * R + r) * run_stride;
+    float2 carry[NR * 4];
+#pragma unroll
+    for (int q = 0; q < NR * 4; ++q) carry[q] = make_float2(0.f, 0.f);
+    if (lane == 0) {
+      tma::expect_bytes(bar, SM::MAG_BYTES);
+      tma::load(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, SM::MAG_BYTES, bar);
+    }
+    const int nrun = te - tb;
+    if (!INIT && lane == 0 && nrun > 1) {
+      tma::expect_bytes(xbar + 1, ring_bytes);
+      tma::load(xs + 2 * HOP, xrun + HOP, HOP * 4, xbar + 1);
+      if (USE_PREV) tma::load(xs + 3 * HOP, prun + HOP, HOP * 4, xbar + 1);
+    }
+#pragma unroll 1
+    for (int t = tb; t < te; ++t) {
+      const int c = t - tb;
+      float2 v[G::NV];
+      float2 wA[R3], wB[R3];
+      if (!INIT) {
+      // ---- stage the frame: v[8 r + n1] = d[(lane + 32 r) + NB n1], n1 < 4 from hop-block t, n1 >= 4 from hop-block t + 1 ----
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = t + h, cs = c + h;
+        const float2* wtab = h ? WB : WA;
+        if (j == 0 || j == T) {  // reflect-padded edge of the clip
+          __syncwarp();
+          reg_stage_reflect<HOP>(a.xin, USE_PREV ? a.xprev : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, R, n, T, j,
+                                 reinterpret_cast<float*>(S), lane);
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = lane + 32 * rr;
+              v[8 * rr + 4 * h + q] = (G::FULL || i < NB) ? S[i + NB * q] : make_float2(0.f, 0.f);
+            }
+        } else if (cs >= 1 && cs <= nrun - 1) {  // interior block of this run: in the shared-memory ring
+          if (h == 1) {
+            if (cs & 1) { tma::wait(xbar + 1, xuse1 & 1); ++xuse1; } else { tma::wait(xbar, xuse0 & 1); ++xuse0; }
+          }
+          const float2* src = reinterpret_cast<const float2*>(xs + (cs & 1) * 2 * HOP);
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = lane + 32 * rr;
+              float2 xv = make_float2(0.f, 0.f);
+              if (G::FULL || i < NB) {
+                xv = src[i + NB * q];
+                if (USE_PREV) xv = cfma2(src[H2 + i + NB * q], nmom, xv);
+                xv = cscale2(xv, wtab[i + NB * q]);
+              }
+              v[8 * rr + 4 * h + q] = xv;
+            }
+        } else {  // block on a run boundary: the sum of this run's slot and the neighbouring run's slot
+          const size_t o1 = (size_t)cs * HOP;
+          const ptrdiff_t o2 = (cs == 0) ? -(ptrdiff_t)run_stride + (ptrdiff_t)n * HOP : (ptrdiff_t)run_stride;
+          const bool two = (cs == 0) || (j == te);
+          const float2* p1 = reinterpret_cast<const float2*>(xrun + o1);
+          const float2* q1 = reinterpret_cast<const float2*>(prun + o1);
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = lane + 32 * rr;
+              float2 xv = make_float2(0.f, 0.f);
+              if (G::FULL || i < NB) {
+                const int m = i + NB * q;
+                xv = p1[m];
+                if (two) xv = cadd(xv, reinterpret_cast<const float2*>(xrun + o2)[m]);
+                if (USE_PREV) {
+                  float2 pv = q1[m];
+                  if (two) pv = cadd(pv, reinterpret_cast<const float2*>(prun + o2)[m]);
+                  xv = cfma2(pv, nmom, xv);
+                }
+                xv = cscale2(xv, wtab[m]);
+              }
+              v[8 * rr + 4 * h + q] = xv;
+            }
+        }
+      }
+      {  // block c is consumed: its ring slot takes block c + 2 while this frame computes
+        __syncwarp();
+        if (lane == 0 && c + 2 <= nrun - 1) {
+          float* slot = xs + (c & 1) * 2 * HOP;
+          tma::expect_bytes(xbar + (c & 1), ring_bytes);
+          tma::load(slot, xrun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
+          if (USE_PREV) tma::load(slot + HOP, prun + (size_t)(c + 2) * HOP, HOP * 4, xbar + (c & 1));
+        }
+      }
+      // ---- forward FFT ----
+      __syncwarp();
+      fwd1_store_r<R3>(lane, v, tw, S);
+      __syncwarp();
+      fwd2_load_r<R3>(lane, v, S);
+      __syncwarp();
+      fwd2_store_r<R3>(lane, v, tw, S);
+      __syncwarp();
+      fwd3_load_r<R3>(lane, wA, wB, S);
+      }
+      // ---- projection to unit modulus, x mag (INIT: mag x initial angles) ----
+      tma::wait(bar, tma_uses & 1);
+      ++tma_uses;
+      if (INIT) {
+        const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+        init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
+      } else {
+        project_frame<R3>(lane, wA, wB, RT, mg_s);
+      }
+      __syncwarp();  // every lane is done reading the staged row
+      if (lane == 0 && t + 1 < te) {
+        tma::expect_bytes(bar, SM::MAG_BYTES);
+        tma::load(mg_s, a.mag_tf + ((size_t)b * T + t + 1) * a.Fp, SM::MAG_BYTES, bar);
+      }
+      // ---- inverse FFT ----
+      inv1_store_r<R3>(lane, wA, wB, S);
+      __syncwarp();
+      inv2_load_r<R3>(lane, v, tw, S);
+      __syncwarp();
+      inv2_store_r<R3>(lane, v, S);
+      __syncwarp();
+      inv3_load_r<R3>(lane, v, tw, S);
+      // ---- synthesis window + overlap-add: block c = carry + first half ; carry = second half ----
+      const bool direct = (a.wave != nullptr && c >= 1);  // last iteration, block interior to this run: final samples
+      const float sc = (direct && a.out_scale) ? a.out_scale[b] : 1.0f;
+      float2* dst = direct ? reinterpret_cast<float2*>(a.wave + (size_t)b * HOP * (T - 1) + (size_t)(t - 1) * HOP)
+                           : reinterpret_cast<float2*>(xo + (size_t)c * HOP);
+      const float2* ie = reinterpret_cast<const float2*>(a.inv_env);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = lane + 32 * rr;
+          if (G::FULL || i < NB) {
+            const int m = i + NB * q;
+            float2 o = cfma2(v[8 * rr + q], WN[m], carry[4 * rr + q]);
+            if (direct) o = cscale2(o, cscale2(ie[m], make_float2(sc, sc)));
+            dst[m] = o;
+            carry[4 * rr + q] = cscale2(v[8 * rr + 4 + q], WN[H2 + m]);
+          }
+        }
+    }
+    float2* dl = reinterpret_cast<float2*>(xo + (size_t)(te - tb) * HOP);
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * rr;
+        if (G::FULL || i < NB) dl[i + NB * q] = carry[4 * rr + q];
+      }
+    __syncwarp();
+  }
+}
+
+// warps per CTA: as many as registers (65536 / warps / 32 per thread) and shared memory allow
+template <int R3> struct RegWarps;
+template <> struct RegWarps<5> { static constexpr int W = 16; };    // 128 registers / thread
+template <> struct RegWarps<12> { static constexpr int W = 9; };    // 22.3 KB of staging per warp
+
+int gl_reg_r3(const b2d_plan* p) {
+  if (p->hop * 2 != p->n_fft) return 0;
+  if (p->n_fft == 640) return 5;
+  if (p->n_fft == 1536) return 12;
+  return 0;
+}
+int gl_reg_warps(const b2d_plan* p) {
+  const int r3 = gl_reg_r3(p);
+  return r3 == 5 ? RegWarps<5>::W : r3 == 12 ? RegWarps<12>::W : 0;
+}
+
+template <int R3, int MODE>
+static int launch_reg(const GlRegArgs& a, int num_sms, cudaStream_t st) {
+  constexpr int W = RegWarps<R3>::W;
+  const size_t smem = (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)W * RegSmem<R3>::WARP_BYTES;
+  static_assert(RegSmem<R3>::TABLE_BYTES + W * RegSmem<R3>::WARP_BYTES <= 232448, "per-CTA shared memory exceeds 227 KB");
+  B2D_SMEM_OPT_IN(smem, gl_reg_kernel<R3, W, MODE>);
+  const int runs = a.B * a.R;
+  gl_reg_kernel<R3, W, MODE><<<runs < num_sms ? runs : num_sms, W * 32, smem, st>>>(a);
+  B2D_LAUNCH_CHECK("gl_reg_kernel");
+  return B2D_OK;
+}
+template <int MODE>
+static int launch_reg_r3(const b2d_plan* p, const GlRegArgs& a, cudaStream_t st) {
+  switch (gl_reg_r3(p)) {
+    case 5: return launch_reg<5, MODE>(a, p->num_sms, st);
+    case 12: return launch_reg<12, MODE>(a, p->num_sms, st);
+  }
+  return fail(B2D_ERR_UNSUPPORTED, "no register-FFT Griffin-Lim kernel for n_fft = %d", p->n_fft);
+}
+static GlRegArgs reg_args(const b2d_plan* p, const float* mag_tf, int B, int T, int n, int R) {
+  GlRegArgs a{};
+  a.mag_tf = mag_tf; a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  return a;
+}
+
+int launch_gl_reg(const b2d_plan* p, const float* mag_tf, const float* xin, const float* xprev, float* xout, int B, int T, int n,
+                  int R, float mom, int use_prev, float* wave, const float* out_scale, cudaStream_t st) {
+  GlRegArgs a = reg_args(p, mag_tf, B, T, n, R);
+  a.xin = xin; a.xprev = use_prev ? xprev : xin; a.xout = xout;
+  a.mom = mom; a.wave = wave; a.out_scale = out_scale;
+  return use_prev ? launch_reg_r3<MODE_ITER>(p, a, st) : launch_reg_r3<MODE_FIRST>(p, a, st);
+}
+// x_0 = istft(mag * angles_0), angles_0 all ones (seed 0) or drawn in-kernel (same draws as the generic kernel for the same seed)
+int launch_gl_reg_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
+                       const unsigned long long* seed_ptr, cudaStream_t st) {
+  GlRegArgs a = reg_args(p, mag_tf, B, T, n, R);
+  a.xin = xout; a.xprev = xout; a.xout = xout; a.seed = seed; a.seed_ptr = seed_ptr;
+  return launch_reg_r3<MODE_INIT>(p, a, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 for the same lengths: one warp per frame -- window, register FFT, |.|, mel, log1p (the n_fft = 1024 kernel
+// stft_fast512_kernel of gl_fast.cu with the generic last radix).  Interior frames (contiguous, 16-byte aligned in the clip)
+// arrive by TMA into a two-slot per-warp ring one frame ahead; the reflect-padded edge frames are staged by the warp.
+// ------------------------------------------------------------------------------------------------
+struct StftRegArgs {
+  const float* wave;
+  const float* inv_scale;
+  int B, L, T, n_mels;
+  const float2* tw;
+  const float2* rtw;
+  const float* win;
+  const float* seg_w;     // [2][seg_pad][4] mel column segments of <= 8 bins (see b2d_plan)
+  const int* seg_lo;      // [seg_pad]
+  const int* seg_first;   // [n_mels + 1]
+  int seg_pad;
+  float* logmel_bt;
+  int exact_sqrt, exact_div;
+};
+template <int R3> struct StftRegWarps;
+template <> struct StftRegWarps<5> { static constexpr int W = 16; };
+template <> struct StftRegWarps<12> { static constexpr int W = 10; };
+
+template <int R3, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) stft_reg_kernel(const StftRegArgs a) {
+  typedef Geo<R3> G;
+  constexpr int M = G::M, N = G::N, HOP = G::HOP, NB = G::NB, NR = G::NR;
+  constexpr int WSMEM = G::XCH * 8 + 2 * N * 4 + 16;  // exchange | two frame buffers | two mbarriers
+  constexpr int PBASE = (M + 16 + 3) & ~3;            // segment partial sums live behind the magnitudes in the exchange buffer
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WIN = reinterpret_cast<float2*>(smem_raw);  // [M] window pairs
+  float2* RT = WIN + M;                               // [M]
+  float4* SEGW = reinterpret_cast<float4*>(RT + M);   // [2][seg_pad]
+  int* SEGLO = reinterpret_cast<int*>(SEGW + 2 * a.seg_pad);
+  int* SEGF = SEGLO + a.seg_pad;
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(SEGF + ((a.n_mels + 4) & ~3));
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    WIN[i] = make_float2(a.win[2 * i], a.win[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  for (int i = threadIdx.x; i < 2 * a.seg_pad; i += blockDim.x) SEGW[i] = reinterpret_cast<const float4*>(a.seg_w)[i];
+  for (int i = threadIdx.x; i < a.seg_pad; i += blockDim.x) SEGLO[i] = a.seg_lo[i];
+  for (int i = threadIdx.x; i <= a.n_mels; i += blockDim.x) SEGF[i] = a.seg_first[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wsm = warp_base + (size_t)warp * WSMEM;
+  float2* S = reinterpret_cast<float2*>(wsm);
+  float* Sf = reinterpret_cast<float*>(S);
+  float* fbuf = reinterpret_cast<float*>(wsm + G::XCH * 8);  // [2][N]
+  uint64_t* fbar = reinterpret_cast<uint64_t*>(wsm + G::XCH * 8 + 2 * N * 4);
+  if (lane == 0) {
+    tma::barrier_init(fbar, 1);
+    tma::barrier_init(fbar + 1, 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+  LaneTwR<R3> tw;
+  lane_twiddles_r<R3>(lane, a.tw, tw);
+  const unsigned nframes = (unsigned)a.B * (unsigned)a.T;
+  const unsigned stride = gridDim.x * WARPS;
+  const bool tma_ok = (a.L % 4) == 0;  // 16-byte aligned clip rows
+  auto interior = [&](unsigned b, unsigned t, const float*& src) {
+    const long s0 = (long)t * HOP - HOP;
+    src = a.wave + (size_t)b * a.L + s0;
+    return tma_ok && s0 >= 0 && s0 + N <= a.L;
+  };
+  uint32_t use0 = 0, use1 = 0;
+  unsigned f = blockIdx.x * WARPS + warp;
+  unsigned b = f / (unsigned)a.T, t = f - b * (unsigned)a.T;
+  int slot = 0;
+  if (f < nframes && lane == 0) {
+    const float* src;
+    if (interior(b, t, src)) { tma::expect_bytes(fbar, N * 4); tma::load(fbuf, src, N * 4, fbar); }
+  }
+  unsigned bn = 0, tn = 0;
+#pragma unroll 1
+  for (; f < nframes; f += stride, slot ^= 1, b = bn, t = tn) {
+    const float* x = a.wave + (size_t)b * a.L;
+    const float pk = a.inv_scale ? a.inv_scale[b] : 1.0f;
+    const float rsc = 1.0f / pk;  // x / peak as x * (1 / peak): within one ulp of the division (exact_div: the division itself)
+    float* cur = fbuf + slot * N;
+    const float* src_cur;
+    const bool cur_tma = interior(b, t, src_cur);
+    bn = (f + stride) / (unsigned)a.T;
+    tn = (f + stride) - bn * (unsigned)a.T;
+    if (lane == 0 && f + stride < nframes) {  // next frame of this warp into the other slot
+      const float* src;
+      if (interior(bn, tn, src)) { tma::expect_bytes(fbar + (slot ^ 1), N * 4); tma::load(fbuf + (slot ^ 1) * N, src, N * 4, fbar + (slot ^ 1)); }
+    }
+    if (cur_tma) {
+      if (slot) { tma::wait(fbar + 1, use1 & 1); ++use1; } else { tma::wait(fbar, use0 & 1); ++use0; }
+    } else {  // reflect-padded edge frame (or unaligned clip length): stage it here
+      const long s0 = (long)t * HOP - HOP;
+      for (int i = lane; i < N; i += 32) {
+        long sidx = s0 + i;
+        if (sidx < 0) sidx = -sidx;
+        if (sidx >= a.L) sidx = 2L * (a.L - 1) - sidx;
+        cur[i] = (sidx >= 0 && sidx < a.L) ? x[sidx] : 0.f;
+      }
+      __syncwarp();
+    }
+    float2 v[G::NV];
+    {
+      const float2* c2 = reinterpret_cast<const float2*>(cur);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = lane + 32 * rr;
+          float2 xv = make_float2(0.f, 0.f);
+          if (G::FULL || i < NB) {
+            const int m = i + NB * q;
+            xv = c2[m];
+            xv = a.exact_div ? make_float2(xv.x / pk, xv.y / pk) : cscale2(xv, make_float2(rsc, rsc));
+            xv = cscale2(xv, WIN[m]);
+          }
+          v[8 * rr + q] = xv;
+        }
+    }
+    __syncwarp();
+    fwd1_store_r<R3>(lane, v, tw, S);
+    __syncwarp();
+    fwd2_load_r<R3>(lane, v, S);
+    __syncwarp();
+    fwd2_store_r<R3>(lane, v, tw, S);
+    __syncwarp();
+    float2 wA[R3], wB[R3], U[R3], V[R3];
+    fwd3_load_r<R3>(lane, wA, wB, S);
+    __syncwarp();  // the exchange buffer is re-used for the magnitudes
+    gather_pairs<R3>(lane, wA, wB, U, V);
+#pragma unroll
+    for (int r = 0; r < R3; ++r) {
+      const int k = slot_k_r<R3>(lane, r);
+      if (r == 0 && lane == 0) {
+        Sf[0] = fabsf(U[0].x + U[0].y);
+        Sf[M] = fabsf(U[0].x - U[0].y);
+        const float sh = V[0].x * V[0].x + V[0].y * V[0].y;
+        Sf[M / 2] = sqrtf(sh);
+      } else {
+        float2 xk, xmk;
+        rfft_split(U[r], V[r], RT[k], xk, xmk);
+        const float s1 = xk.x * xk.x + xk.y * xk.y, s2 = xmk.x * xmk.x + xmk.y * xmk.y;
+        Sf[k] = sqrtf(s1);
+        Sf[M - k] = sqrtf(s2);
+      }
+    }
+    if (lane < 8) Sf[M + 1 + lane] = 0.f;  // the zero-weight taps of a column's last segment read up to 7 bins past the Nyquist bin
+    __syncwarp();
+    float* P = Sf + PBASE;
+    for (int s0 = 0; s0 < a.seg_pad; s0 += 32) {  // lane s accumulates segment s (<= 8 consecutive bins of one mel column) ...
+      const int sg = s0 + lane;
+      const float* mp = Sf + SEGLO[sg];
+      const float4 w0 = SEGW[sg], w1 = SEGW[a.seg_pad + sg];
+      float acc = mp[0] * w0.x;
+      acc = fmaf(mp[1], w0.y, acc); acc = fmaf(mp[2], w0.z, acc); acc = fmaf(mp[3], w0.w, acc);
+      acc = fmaf(mp[4], w1.x, acc); acc = fmaf(mp[5], w1.y, acc); acc = fmaf(mp[6], w1.z, acc); acc = fmaf(mp[7], w1.w, acc);
+      P[sg] = acc;
+    }
+    __syncwarp();
+    for (int m = lane; m < a.n_mels; m += 32) {  // ... then every mel column sums its segments in order
+      float acc = 0.f;
+      for (int sg = SEGF[m]; sg < SEGF[m + 1]; ++sg) acc += P[sg];
+      a.logmel_bt[(size_t)f * a.n_mels + m] = log1pf(acc);
+    }
+    __syncwarp();
+  }
+}
+
+template <int R3>
+static int launch_stft_reg_t(const b2d_plan* p, const StftRegArgs& a, cudaStream_t st) {
+  constexpr int W = StftRegWarps<R3>::W;
+  typedef Geo<R3> G;
+  const size_t smem = sizeof(float2) * 2 * G::M + (size_t)p->mel_seg_pad * 36 + sizeof(int) * ((p->n_mels + 4) & ~3) +
+                      (size_t)W * (G::XCH * 8 + 2 * G::N * 4 + 16);
+  B2D_REQUIRE(smem <= 232448, B2D_ERR_UNSUPPORTED, "mel filterbank too dense for the register STFT kernel");
+  B2D_SMEM_OPT_IN(smem, stft_reg_kernel<R3, W>);
+  const size_t nframes = (size_t)a.B * a.T;
+  const size_t want = (nframes + W - 1) / W;
+  const int grid = (int)(want < (size_t)p->num_sms ? want : (size_t)p->num_sms);
+  stft_reg_kernel<R3, W><<<grid, W * 32, smem, st>>>(a);
+  B2D_LAUNCH_CHECK("stft_reg_kernel");
+  return B2D_OK;
+}
+
+bool stft_reg_supported(const b2d_plan* p, int B, int L) {
+  return gl_reg_r3(p) != 0 && L >= p->n_fft && p->n_mels <= 128 && p->mel_seg_pad <= 320 && (long long)B * (1 + L / p->hop) < (1ll << 30);
+}
+int launch_stft_reg(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt, cudaStream_t st) {
+  StftRegArgs a;
+  a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.n_mels = p->n_mels;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win;
+  a.seg_w = p->d_seg_w; a.seg_lo = p->d_seg_lo; a.seg_first = p->d_seg_first; a.seg_pad = p->mel_seg_pad;
+  a.logmel_bt = logmel_bt;
+  a.exact_sqrt = (p->flags & B2D_PLAN_EXACT_SQRT) ? 1 : 0;
+  a.exact_div = (p->flags & B2D_PLAN_EXACT_PEAK_DIV) ? 1 : 0;
+  return gl_reg_r3(p) == 5 ? launch_stft_reg_t<5>(p, a, st) : launch_stft_reg_t<12>(p, a, st);
+}
+
+}  // namespace b2d

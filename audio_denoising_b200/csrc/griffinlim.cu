@@ -281,6 +281,12 @@ int gl_warp_warps(const b2d_plan* p);
 bool gl_warp_supported(const b2d_plan* p);
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            const unsigned long long* seed_ptr, cudaStream_t st);
+int launch_gl_reg(const b2d_plan* p, const float* mag_tf, const float* xin, const float* xprev, float* xout, int B, int T, int n,
+                  int R, float mom, int use_prev, float* wave, const float* out_scale, cudaStream_t st);  // gl_reg.cu
+int launch_gl_reg_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
+                       const unsigned long long* seed_ptr, cudaStream_t st);
+int gl_reg_r3(const b2d_plan* p);
+int gl_reg_warps(const b2d_plan* p);
 
 // uniform cut for the generic shared-memory kernel: one CTA per run, runs a multiple of G frames long
 static GlPartition generic_partition(const b2d_plan* p, int B, int T) {
@@ -310,7 +316,8 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
     if (p->n_fft == 1024 && p->hop == 512) q.fast = 1;
     if (p->n_fft == 512 && p->hop == 256) q.fast = 2;
     if (p->n_fft == 2048 && p->hop == 1024) q.fast = 3;
-    // every other length with hop = n_fft / 2 (640, 1536 ...): warp-synchronous Stockham kernel (gl_warp.cu)
+    if (gl_reg_r3(p)) q.fast = 5;  // n_fft 640 / 1536: generic-radix register FFT (gl_reg.cu)
+    // every other length with hop = n_fft / 2: warp-synchronous Stockham kernel (gl_warp.cu)
     if (!q.fast && gl_warp_supported(p)) q.fast = 4;
   }
   if (q.fast) {
@@ -320,7 +327,7 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
     // (Measured dead ends, round 1: dealing the runs longest-first in serpentine order, and a balanced run table of equal
     //  shares split at clip boundaries -- both correct, both 4-10 % slower: 1536 busy warps already saturate the SMs' issue /
     //  shared-memory throughput, more runs only add boundary traffic.)
-    const int wps = q.fast == 3 ? gl_fast_n2048_warps() : q.fast == 4 ? gl_warp_warps(p) : gl_fast_warps_per_sm();
+    const int wps = q.fast == 3 ? gl_fast_n2048_warps() : q.fast == 4 ? gl_warp_warps(p) : q.fast == 5 ? gl_reg_warps(p) : gl_fast_warps_per_sm();
     const long slots = (long)wps * p->num_sms;
     const int min_run = 2;  // frames per run: short runs cut the latency of small batches
     const int maxR = (T + min_run - 1) / min_run;
@@ -346,12 +353,12 @@ static size_t part_floats(const b2d_plan* p, const GlPartition& q, int B) {
   return (size_t)B * q.R * (q.n + 1) * p->hop;
 }
 
-// workspace: the n_fft = 1024 fast path keeps three time-domain iterates (x_{k-1}, x_k, x_{k+1}) and no spectrogram state;
+// workspace: the time-domain-momentum fast paths (n_fft 1024; 640 / 1536) keep three time-domain iterates (x_{k-1}, x_k, x_{k+1}) and no spectrogram state;
 // the other kernels keep two iterates and the complex `tprev` [B, T, M]
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   const GlPartition q = gl_partition(p, B, T);
   const size_t pbytes = align_up(part_floats(p, q, B) * sizeof(float), 256);
-  size_t bytes = (q.fast == 1) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
+  size_t bytes = (q.fast == 1 || q.fast == 5) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
   if (need_mag_copy) bytes += align_up((size_t)B * T * p->Fp * sizeof(float), 256);
   return bytes;
 }
@@ -370,7 +377,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   unsigned char* base = static_cast<unsigned char*>(ws);
   float* xa = reinterpret_cast<float*>(base);
   float* xb = reinterpret_cast<float*>(base + pbytes);
-  float* xc = reinterpret_cast<float*>(base + 2 * pbytes);       // fast == 1: third iterate
+  float* xc = reinterpret_cast<float*>(base + 2 * pbytes);       // fast == 1 / 5: third iterate
   float2* tprev = reinterpret_cast<float2*>(base + 2 * pbytes);  // otherwise: complex spectrogram state
 
   GlArgs a;
@@ -413,6 +420,8 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     if ((rc = launch_gl_fast512_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st))) return rc;
   } else if (q.fast == 3 && init_angles == nullptr) {
     if ((rc = launch_gl_fast_n2048_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st))) return rc;
+  } else if (q.fast == 5 && init_angles == nullptr) {
+    if ((rc = launch_gl_reg_init(p, mag_tf, xa, B, T, q.n, q.R, seed, seed_ptr, st))) return rc;
   } else {
     if ((rc = launch_generic(grid, a))) return rc;
     B2D_LAUNCH_CHECK("gl_generic_kernel(init)");
@@ -423,9 +432,11 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
     a.store_prev = (it + 1 < n_iter && a.mom != 0.f) ? 1 : 0;
     a.xin = cur; a.xout = nxt;
     const bool last = (it + 1 == n_iter);  // last iteration: run-interior hop-blocks go straight to `wave`
-    if (q.fast == 1) {
+    if (q.fast == 1 || q.fast == 5) {
       // time-domain momentum: reads x_k (cur) and x_{k-1} (prv), writes x_{k+1} (nxt); three buffers rotate
-      if ((rc = launch_gl_fast512(p, mag_tf, cur, prv, nxt, B, T, q.n, q.R, a.mom, a.use_prev, last ? wave : nullptr, out_scale, st))) return rc;
+      if (q.fast == 1) rc = launch_gl_fast512(p, mag_tf, cur, prv, nxt, B, T, q.n, q.R, a.mom, a.use_prev, last ? wave : nullptr, out_scale, st);
+      else rc = launch_gl_reg(p, mag_tf, cur, prv, nxt, B, T, q.n, q.R, a.mom, a.use_prev, last ? wave : nullptr, out_scale, st);
+      if (rc) return rc;
       direct_interior = last;
       float* t = prv; prv = cur; cur = nxt; nxt = t;
       continue;

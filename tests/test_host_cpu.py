@@ -154,11 +154,11 @@ def test_two_rank_gloo_sharded_driver():
 
 
 def test_host_fft_and_fast_path_index_math():
-    """csrc/fft.cuh and csrc/gl_fast.cuh are __host__ __device__: run their unit tests on the CPU."""
+    """csrc/fft.cuh, csrc/gl_fast.cuh and csrc/gl_reg.cuh are __host__ __device__: run their unit tests on the CPU."""
     nvcc = "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    for name in ["fft_host_test", "gl_fast_host_test"]:
+    for name in ["fft_host_test", "gl_fast_host_test", "gl_reg_host_test"]:
         exe = os.path.join("/tmp", f"b2d_{name}")
         r = subprocess.run([nvcc, "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", name + ".cu")], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
