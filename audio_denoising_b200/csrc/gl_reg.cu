@@ -45,15 +45,16 @@ struct RegSmem {
 };
 
 // sample `is` of interior hop-block js of clip b in the partial format: the sum of two slots on a run boundary
+// (the loads go to L2 with ld.global.cg: in the single-launch kernel `part` was written by other CTAs of the cluster a step ago)
 template <int HOP>
-__device__ __forceinline__ float reg_partial_sample(const float* __restrict__ part, int b, int R, int n, int js, int is) {
+__device__ __forceinline__ float reg_partial_sample(const float* part, int b, int R, int n, int js, int is) {
   const int r1 = (js - 1) / n, r2 = js / n;
-  float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
-  if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
+  float v = __ldcg(part + ((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is);
+  if (r2 != r1) v += __ldcg(part + ((size_t)(b * R + r2) * (n + 1)) * HOP + is);
   return v;
 }
 template <int HOP>
-__device__ __noinline__ void reg_stage_reflect(const float* __restrict__ part, const float* __restrict__ prev, float mom,
+__device__ __noinline__ void reg_stage_reflect(const float* part, const float* prev, float mom,
                                                const float* __restrict__ inv_env, const float* __restrict__ win_half, int b, int R,
                                                int n, int T, int j, float* __restrict__ dst, int lane) {
   for (int i = lane; i < HOP; i += 32) {
@@ -530,6 +531,324 @@ int launch_stft_reg(const b2d_plan* p, const float* wave, const float* inv_scale
   a.exact_sqrt = (p->flags & B2D_PLAN_EXACT_SQRT) ? 1 : 0;
   a.exact_div = (p->flags & B2D_PLAN_EXACT_PEAK_DIV) ? 1 : 0;
   return gl_reg_r3(p) == 5 ? launch_stft_reg_t<5>(p, a, st) : launch_stft_reg_t<12>(p, a, st);
+}
+
+
+// reflect-padded edge block with every load in flight at once (the single-launch kernel has no other warps to hide a
+// serial chain of L2 round trips behind: the compact loop above costs ~6 us there)
+template <int HOP>
+__device__ __forceinline__ void reg_stage_reflect_wide(const float* part, const float* prev, float mom, const float* __restrict__ inv_env,
+                                                       const float* __restrict__ win_half, int b, int R, int n, int T, int j, float* dst,
+                                                       int lane) {
+  constexpr int PER = HOP / 32;
+  float v[PER], pv[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int i = lane + 32 * q;
+    int js, is;
+    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
+    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
+    v[q] = reg_partial_sample<HOP>(part, b, R, n, js, is);
+    pv[q] = prev ? reg_partial_sample<HOP>(prev, b, R, n, js, is) : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int i = lane + 32 * q;
+    const int is = (j == 0) ? ((i == 0) ? 0 : HOP - i) : ((i == HOP - 1) ? HOP - 1 : HOP - 2 - i);
+    dst[i] = fmaf(-mom, pv[q], v[q]) * inv_env[is] * win_half[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small problems in ONE launch: a streaming hop (T = 3 frames per session, app3.py:213) or a handful of whole clips
+// (BASELINE config 1: one 4 s clip; the B <= 16 points of the config-5 sweep).  Per-iteration launches are launch-bound
+// there (12 us per iteration for one clip).  Here a clip belongs to one thread-block CLUSTER: its runs are dealt over the
+// cluster's warps (one frame per warp when the clip has at most 8 x WARPS frames), the init and all n_iter iterations run
+// inside the kernel, separated by barrier.cluster (release / acquire: the iterates live in global memory, i.e. in L2, and
+// cross CTA boundaries at run edges).  Same arithmetic and same partial hop-block format as the batch kernel above.
+// ------------------------------------------------------------------------------------------------
+struct GlRegFusedArgs {
+  const float* mag_tf;      // [B,T,Fp]
+  const float2* angles0;    // [B,F,T] torch layout or null
+  float* x[3];              // three iterates, partial hop-block format
+  int B, T, n, R, Fp, F, n_iter, csize;
+  const float2* tw;
+  const float2* rtw;
+  const float* win;
+  const float* winn;
+  const float* inv_env;
+  float mom;
+  float* wave;              // [B, HOP*(T-1)]
+  const float* out_scale;   // [B] or null
+  unsigned long long seed;
+  const unsigned long long* seed_ptr;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("fence.proxy.async;\n" ::: "memory");  // this thread's global writes -> visible to the TMA (async proxy) reads of the next step
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int R3>
+struct FusedSmem {  // per warp: exchange | mag row | mbarrier  (no iterate ring: every hop-block is a run-boundary block when n == 1)
+  typedef Geo<R3> G;
+  static constexpr int OFF_MAG = G::XCH * 8;
+  static constexpr int OFF_BAR = OFF_MAG + ((RegSmem<R3>::MAG_BYTES + 15) & ~15);
+  static constexpr int WARP_BYTES = OFF_BAR + 16;
+};
+
+template <int R3, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_fused_kernel(const GlRegFusedArgs a) {
+  typedef Geo<R3> G;
+  typedef FusedSmem<R3> SM;
+  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2;
+  constexpr int MAG_BYTES = RegSmem<R3>::MAG_BYTES;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WA = reinterpret_cast<float2*>(smem_raw);
+  float2* WB = WA + H2;
+  float2* WN = WB + H2;
+  float2* RT = WN + M;
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + M);
+  for (int i = threadIdx.x; i < H2; i += blockDim.x) {
+    WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
+    WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;  // one frame per run: R == T, n == 1; run r owns slots 2 r (first half of frame r) and 2 r + 1 (second half)
+  const int b = (int)blockIdx.x / a.csize, crank = (int)blockIdx.x % a.csize;
+  const int t = crank * WARPS + warp;  // this warp's frame
+  const bool active = t < T;
+  unsigned char* wsm = warp_base + (size_t)warp * SM::WARP_BYTES;
+  float2* S = reinterpret_cast<float2*>(wsm);
+  float* mg_s = reinterpret_cast<float*>(wsm + SM::OFF_MAG);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + SM::OFF_BAR);
+  if (lane == 0) {
+    tma::barrier_init(bar, 1);
+    tma::fence_barrier_init();
+    if (active) {  // the frame's magnitude row: loaded once, resident for the init and all iterations
+      tma::expect_bytes(bar, MAG_BYTES);
+      tma::load(mg_s, a.mag_tf + ((size_t)b * T + t) * a.Fp, MAG_BYTES, bar);
+    }
+  }
+  __syncwarp();
+  LaneTwR<R3> tw;
+  lane_twiddles_r<R3>(lane, a.tw, tw);
+  const float2 nmom = make_float2(-a.mom, -a.mom);
+  const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+  const size_t clip = (size_t)b * T * 2 * HOP;  // this clip's slots in an iterate buffer
+  if (active) tma::wait(bar, 0);
+
+#pragma unroll 1
+  for (int step = 0; step <= a.n_iter; ++step) {
+    const bool init = (step == 0);
+    const bool use_prev = (step >= 2) && (a.mom != 0.f);
+    const float* xin = a.x[(step + 2) % 3] + clip;    // x_k       (written by step - 1)
+    const float* xprev = a.x[(step + 1) % 3] + clip;  // x_{k-1}   (written by step - 2)
+    float* xout = a.x[step % 3] + clip;
+    if (active) {
+      float2 v[G::NV];
+      float2 wA[R3], wB[R3];
+      if (!init) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = t + h;  // padded hop-block index: block j = slot (2 (j - 1) + 1) + slot (2 j), 1 <= j <= T - 1
+          const float2* wtab = h ? WB : WA;
+          if (j == 0 || j == T) {
+            __syncwarp();
+            reg_stage_reflect_wide<HOP>(xin - clip, use_prev ? xprev - clip : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, T, 1, T, j,
+                                        reinterpret_cast<float*>(S), lane);
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int i = lane + 32 * rr;
+                v[8 * rr + 4 * h + q] = (G::FULL || i < NB) ? S[i + NB * q] : make_float2(0.f, 0.f);
+              }
+          } else {
+            const float2* p1 = reinterpret_cast<const float2*>(xin + (size_t)(2 * j - 1) * HOP);   // second half of frame j - 1
+            const float2* p2 = reinterpret_cast<const float2*>(xin + (size_t)(2 * j) * HOP);       // first half of frame j
+            const float2* q1 = reinterpret_cast<const float2*>(xprev + (size_t)(2 * j - 1) * HOP);
+            const float2* q2 = reinterpret_cast<const float2*>(xprev + (size_t)(2 * j) * HOP);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int i = lane + 32 * rr;
+                float2 xv = make_float2(0.f, 0.f);
+                if (G::FULL || i < NB) {
+                  const int m = i + NB * q;
+                  xv = cadd(__ldcg(p1 + m), __ldcg(p2 + m));  // written by other warps / CTAs of the cluster one step ago: read from L2
+                  if (use_prev) xv = cfma2(cadd(__ldcg(q1 + m), __ldcg(q2 + m)), nmom, xv);
+                  xv = cscale2(xv, wtab[m]);
+                }
+                v[8 * rr + 4 * h + q] = xv;
+              }
+          }
+        }
+        __syncwarp();
+        fwd1_store_r<R3>(lane, v, tw, S);
+        __syncwarp();
+        fwd2_load_r<R3>(lane, v, S);
+        __syncwarp();
+        fwd2_store_r<R3>(lane, v, tw, S);
+        __syncwarp();
+        fwd3_load_r<R3>(lane, wA, wB, S);
+        project_frame<R3>(lane, wA, wB, RT, mg_s);
+      } else if (a.angles0) {
+        init_frame_angles<R3>(lane, wA, wB, RT, mg_s, a.angles0 + (size_t)b * a.F * T + t, T);
+      } else {
+        init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
+      }
+      __syncwarp();
+      inv1_store_r<R3>(lane, wA, wB, S);
+      __syncwarp();
+      inv2_load_r<R3>(lane, v, tw, S);
+      __syncwarp();
+      inv2_store_r<R3>(lane, v, S);
+      __syncwarp();
+      inv3_load_r<R3>(lane, v, tw, S);
+      float2* d0 = reinterpret_cast<float2*>(xout + (size_t)(2 * t) * HOP);      // slot 0: first half x window
+      float2* d1 = reinterpret_cast<float2*>(xout + (size_t)(2 * t + 1) * HOP);  // slot 1: second half x window
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = lane + 32 * rr;
+          if (G::FULL || i < NB) {
+            const int m = i + NB * q;
+            d0[m] = cscale2(v[8 * rr + q], WN[m]);
+            d1[m] = cscale2(v[8 * rr + 4 + q], WN[H2 + m]);
+          }
+        }
+    }
+    cluster_sync_all();  // x_{k+1} complete and visible to every CTA of the clip's cluster
+  }
+  // ---- stitch: hop-block j (1 .. T-1) = its two partial slots x 1 / envelope x clip scale ----
+  const float* fin = a.x[a.n_iter % 3] + clip;
+  const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
+  for (int j = 1 + t; j <= T - 1; j += a.csize * WARPS) {
+    float* dst = a.wave + (size_t)b * HOP * (T - 1) + (size_t)(j - 1) * HOP;
+    const float* s1 = fin + (size_t)(2 * j - 1) * HOP;
+    const float* s2 = fin + (size_t)(2 * j) * HOP;
+    for (int i = lane; i < HOP; i += 32) dst[i] = (__ldcg(s1 + i) + __ldcg(s2 + i)) * a.inv_env[i] * sc;
+  }
+}
+
+template <int R3> struct FusedWarps;
+template <> struct FusedWarps<4> { static constexpr int W = 16; };
+template <> struct FusedWarps<5> { static constexpr int W = 16; };
+template <> struct FusedWarps<8> { static constexpr int W = 16; };   // 8 x 16 warps: one frame per warp for a 4 s / 16 kHz clip
+template <> struct FusedWarps<12> { static constexpr int W = 12; };
+
+static int fused_r3(const b2d_plan* p) {
+  if (p->hop * 2 != p->n_fft) return 0;
+  switch (p->n_fft) { case 512: return 4; case 640: return 5; case 1024: return 8; case 1536: return 12; }
+  return 0;
+}
+static int fused_warps(int r3) { return r3 == 4 ? FusedWarps<4>::W : r3 == 5 ? FusedWarps<5>::W : r3 == 8 ? FusedWarps<8>::W : FusedWarps<12>::W; }
+
+template <int R3>
+static int launch_fused_t(const b2d_plan* p, const GlRegFusedArgs& a, cudaStream_t st) {
+  constexpr int W = FusedWarps<R3>::W;
+  const size_t smem = (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)W * FusedSmem<R3>::WARP_BYTES;
+  static_assert(RegSmem<R3>::TABLE_BYTES + W * FusedSmem<R3>::WARP_BYTES <= 232448, "per-CTA shared memory exceeds 227 KB");
+  B2D_SMEM_OPT_IN(smem, gl_reg_fused_kernel<R3, W>);
+  if (a.csize > 8) {
+    static std::atomic<int> nonportable{0};
+    if (!nonportable.load()) {
+      B2D_CUDA(cudaFuncSetAttribute(gl_reg_fused_kernel<R3, W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      nonportable.store(1);
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.B * a.csize));
+  cfg.blockDim = dim3(W * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B2D_CUDA(cudaLaunchKernelEx(&cfg, gl_reg_fused_kernel<R3, W>, a));
+  B2D_LAUNCH_CHECK("gl_reg_fused_kernel");
+  return B2D_OK;
+}
+
+// how many clusters of `csize` CTAs of the single-launch kernel the device keeps resident at once (measured on B200: 8 for
+// csize 8 -- one per GPC -- although 16 x 8 CTAs are fewer than the 148 SMs); queried once per (length, cluster size)
+template <int R3>
+static int fused_max_clusters_t(int csize) {
+  constexpr int W = FusedWarps<R3>::W;
+  static std::atomic<int> cache[5];  // csize 1, 2, 4, 8, 16
+  int slot = 0;
+  while ((1 << slot) < csize) ++slot;
+  int v = cache[slot].load();
+  if (v) return v;
+  const size_t smem = (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)W * FusedSmem<R3>::WARP_BYTES;
+  if (cudaFuncSetAttribute(gl_reg_fused_kernel<R3, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  if (csize > 8 && cudaFuncSetAttribute(gl_reg_fused_kernel<R3, W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(W * 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gl_reg_fused_kernel<R3, W>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[slot].store(n > 0 ? n : -1);
+  return n > 0 ? n : -1;
+}
+static int fused_max_clusters(int r3, int csize) {
+  switch (r3) {
+    case 4: return fused_max_clusters_t<4>(csize);
+    case 5: return fused_max_clusters_t<5>(csize);
+    case 8: return fused_max_clusters_t<8>(csize);
+    case 12: return fused_max_clusters_t<12>(csize);
+  }
+  return 0;
+}
+
+// Is the single-launch kernel the right tool?  Yes when a clip's frames fit one warp each in a cluster (<= 16 CTAs) and every
+// clip's cluster is resident at once.  (n == 1, R == T in the partial hop-block format.)
+bool gl_reg_fused_plan(const b2d_plan* p, int B, int T, int* n_out, int* R_out, int* csize_out) {
+  const int r3 = fused_r3(p);
+  if (!r3 || (p->flags & B2D_PLAN_GENERIC_KERNELS)) return false;
+  // a streaming hop (T = 3) stays on the block-cooperative single-launch kernel of griffinlim.cu: 512-1024 threads share
+  // three frames there, which beats one warp per frame on latency (measured 0.25 vs 0.50 ms per 20 ms hop)
+  if (T <= 4) return false;
+  const int W = fused_warps(r3);
+  int csize = 1;
+  while (csize < 16 && csize * W < T) csize *= 2;
+  if (csize * W < T) return false;
+  if (B > fused_max_clusters(r3, csize)) return false;  // a second wave of clusters would cost what the per-iteration launches cost
+  *n_out = 1; *R_out = T; *csize_out = csize;
+  return true;
+}
+
+int launch_gl_reg_fused(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
+                        const unsigned long long* seed_ptr, float* x0, float* x1, float* x2, int B, int T, int n, int R, int csize,
+                        int n_iter, float mom, const float* out_scale, float* wave, cudaStream_t st) {
+  GlRegFusedArgs a{};
+  a.mag_tf = mag_tf; a.angles0 = angles0; a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
+  a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp; a.F = p->F; a.n_iter = n_iter; a.csize = csize;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.mom = mom; a.wave = wave; a.out_scale = out_scale; a.seed = seed; a.seed_ptr = seed_ptr;
+  switch (fused_r3(p)) {
+    case 4: return launch_fused_t<4>(p, a, st);
+    case 5: return launch_fused_t<5>(p, a, st);
+    case 8: return launch_fused_t<8>(p, a, st);
+    case 12: return launch_fused_t<12>(p, a, st);
+  }
+  return fail(B2D_ERR_UNSUPPORTED, "no single-launch Griffin-Lim kernel for n_fft = %d", p->n_fft);
 }
 
 }  // namespace b2d

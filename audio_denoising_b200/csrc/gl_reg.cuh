@@ -299,5 +299,27 @@ B2D_HD void init_frame(int lane, float2* wA, float2* wB, const float2* rt, const
   scatter_pairs<R3>(lane, wA, wB, U, V);
 }
 
+// the same from injected initial angles: ang = &angles0[b, 0, t] of the torch layout [B, F, T] (bin stride T)
+template <int R3>
+B2D_HD void init_frame_angles(int lane, float2* wA, float2* wB, const float2* rt, const float* mg, const float2* ang, int T) {
+  constexpr int M = Geo<R3>::M;
+  float2 U[R3], V[R3];
+#pragma unroll
+  for (int r = 0; r < R3; ++r) {
+    const int k = slot_k_r<R3>(lane, r);
+    if (r == 0 && lane == 0) {
+      const float2 a0 = ang[0], aM = ang[(size_t)M * T], ah = ang[(size_t)(M / 2) * T];
+      const float y0 = mg[0] * a0.x, yM = mg[M] * aM.x, mh = mg[M / 2];
+      U[0] = make_float2(y0 + yM, y0 - yM);
+      V[0] = make_float2(2.0f * mh * ah.x, -2.0f * mh * ah.y);
+    } else {
+      const float2 ak = ang[(size_t)k * T], amk = ang[(size_t)(M - k) * T];
+      const float mk = mg[k], mmk = mg[M - k];
+      irfft_merge(make_float2(mk * ak.x, mk * ak.y), make_float2(mmk * amk.x, mmk * amk.y), rt[k], U[r], V[r]);
+    }
+  }
+  scatter_pairs<R3>(lane, wA, wB, U, V);
+}
+
 }  // namespace regfft
 }  // namespace b2d

@@ -285,6 +285,10 @@ int launch_gl_reg(const b2d_plan* p, const float* mag_tf, const float* xin, cons
                   int R, float mom, int use_prev, float* wave, const float* out_scale, cudaStream_t st);  // gl_reg.cu
 int launch_gl_reg_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                        const unsigned long long* seed_ptr, cudaStream_t st);
+bool gl_reg_fused_plan(const b2d_plan* p, int B, int T, int* n_out, int* R_out, int* csize_out);
+int launch_gl_reg_fused(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
+                        const unsigned long long* seed_ptr, float* x0, float* x1, float* x2, int B, int T, int n, int R, int csize,
+                        int n_iter, float mom, const float* out_scale, float* wave, cudaStream_t st);
 int gl_reg_r3(const b2d_plan* p);
 int gl_reg_warps(const b2d_plan* p);
 
@@ -309,6 +313,9 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   GlPartition q;
   q.G = (p->M <= 1024) ? 4 : 2;
   q.fast = 0;
+  q.csize = 1;
+  // small problems (a streaming hop, a handful of clips): init + all iterations in ONE launch, a cluster per clip (gl_reg.cu)
+  if (gl_reg_fused_plan(p, B, T, &q.n, &q.R, &q.csize)) { q.fast = 6; return q; }
   // a clip of at most one group of frames (a streaming hop: T = 3) runs init + all iterations in ONE launch of the generic
   // kernel, one CTA per clip: faster than 33 launches of the register kernels (n_fft 1024: 0.41 -> 0.3 ms per hop)
   if (T <= q.G) return generic_partition(p, B, T);
@@ -358,7 +365,7 @@ static size_t part_floats(const b2d_plan* p, const GlPartition& q, int B) {
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   const GlPartition q = gl_partition(p, B, T);
   const size_t pbytes = align_up(part_floats(p, q, B) * sizeof(float), 256);
-  size_t bytes = (q.fast == 1 || q.fast == 5) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
+  size_t bytes = (q.fast == 1 || q.fast == 5 || q.fast == 6) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
   if (need_mag_copy) bytes += align_up((size_t)B * T * p->Fp * sizeof(float), 256);
   return bytes;
 }
@@ -406,6 +413,9 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   float* prv = xc;
   bool direct_interior = false;
   int rc;
+  if (q.fast == 6) {
+    return launch_gl_reg_fused(p, mag_tf, init_angles, seed, seed_ptr, xa, xb, xc, B, T, q.n, q.R, q.csize, n_iter, a.mom, out_scale, wave, st);
+  }
   if (!q.fast && q.R == 1 && T <= 16) {
     // short clips (streaming hops: T = 3): every dependency stays inside one CTA -> init + all iterations in one launch
     a.init = 1; a.use_prev = 0; a.store_prev = 0; a.xin = nullptr; a.xout = xa; a.seed = seed; a.seed_ptr = seed_ptr;

@@ -23,7 +23,9 @@ struct GlPartition {
   int R;  // runs per clip
   int G;  // frames per round inside a run
   int fast;  // 0 = generic shared-memory kernel, 1 = n_fft 1024 register kernel, 2 = n_fft 512 (two frames per transform),
-             // 3 = n_fft 2048 (warp pair), 4 = warp-synchronous Stockham (gl_warp.cu), 5 = generic-radix register FFT (gl_reg.cu)
+             // 3 = n_fft 2048 (warp pair), 4 = warp-synchronous Stockham (gl_warp.cu), 5 = generic-radix register FFT (gl_reg.cu),
+             // 6 = the same in a single launch, one cluster of `csize` CTAs per clip (small problems)
+  int csize;
 };
 GlPartition gl_partition(const b2d_plan* p, int B, int T);
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy);

@@ -15,8 +15,10 @@ L = 64000
 noisy = bench.synth_batch(1, L, seed=1234)
 sd, cfg = bench.load_model_weights()
 row = {"config": "1 clip x 4 s @ 16 kHz, n_fft 1024, hop 512, 64 mels, GL 32 it (BASELINE configs[0])", "cpu_count": os.cpu_count()}
+arm = bench.CpuArm()
+pcm1 = bench.to_pcm16(noisy)
 for threads in (1, os.cpu_count()):
-    best = bench.cpu_pass_seconds(1, 5, threads)
+    best = arm.seconds(pcm1, 5, threads)
     row[f"cpu_{threads}_threads_ms"] = round(best * 1e3, 2)
     row[f"cpu_{threads}_threads_audio_s_per_s"] = round(4.0 / best, 1)
 dev = torch.device("cuda:0")
