@@ -8,12 +8,13 @@ interfaces: ``GRUUNet2`` (gruunet2.py), the five torchaudio-style transforms the
 from . import _cabi
 from .checkpoint import TrainingContext, load_denoising_model, save_checkpoint
 from .gruunet2 import GRUUNet, GRUUNet2
+from .momo3 import MOMO3
 from .pipeline import DenoisePipeline, StreamingDenoiser
 from .serving import DenoiseServer
 from .transforms import GriffinLim, InverseMelScale, InverseSpectrogram, MelScale, Resample, Spectrogram, float_to_pcm16, pcm16_to_float
 
 __all__ = [
-    "GRUUNet2", "GRUUNet", "Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram", "Resample", "pcm16_to_float", "float_to_pcm16",
+    "GRUUNet2", "GRUUNet", "MOMO3", "Spectrogram", "MelScale", "InverseMelScale", "GriffinLim", "InverseSpectrogram", "Resample", "pcm16_to_float", "float_to_pcm16",
     "DenoisePipeline", "StreamingDenoiser", "DenoiseServer", "TrainingContext", "load_denoising_model", "save_checkpoint",
     "native_library",
 ]

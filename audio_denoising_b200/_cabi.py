@@ -34,6 +34,20 @@ class ModelConfig(C.Structure):
     ]
 
 
+class CellConfig(C.Structure):
+    _fields_ = [
+        ("arch", C.c_int),
+        ("num_compressed_bins", C.c_int),
+        ("levels", C.c_int),
+        ("num_gaussians", C.c_int),
+        ("n_mels", C.c_int),
+        ("hidden", C.c_int * 8),
+        ("kernel", C.c_int * 8),
+        ("stride", C.c_int * 8),
+        ("padding", C.c_int * 8),
+    ]
+
+
 _vp, _i, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
 
 # name -> (restype, argtypes); mirrors include/b200denoise.h one to one
@@ -50,6 +64,10 @@ SIGNATURES = {
     "b2d_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "b2d_model_destroy": (None, [_vp]),
     "b2d_model_n_mels": (_i, [_vp]),
+    "b2d_cell_create": (_i, [C.POINTER(CellConfig), C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "b2d_cell_destroy": (None, [_vp]),
+    "b2d_cell_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "b2d_cell_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "b2d_peak": (_i, [_vp, _i, _i, _vp, _vp]),
     "b2d_stft": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2d_stft_mel_log1p": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -45,15 +45,26 @@ def _pick_state_dict(ckpt: Any) -> Optional[Mapping[str, torch.Tensor]]:
     return None
 
 
+def _load_checkpoint_file(path: str, trust_pickle: bool):
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        if not trust_pickle:
+            raise
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
 def load_denoising_model(path: str, fallback_config: Optional[Mapping] = None, device: Optional[torch.device] = None,
-                         strict_errors: bool = False, model_class=GRUUNet2):
+                         strict_errors: bool = False, model_class=GRUUNet2, trust_pickle: bool = False):
     """Counterpart of ``load_denoising_model_pytorch`` (app3.py:46-119): returns ``(model.eval() on device, device)`` or
-    ``(None, None)`` when anything is missing or fails -- unless ``strict_errors`` asks for the exception instead."""
+    ``(None, None)`` when anything is missing or fails -- unless ``strict_errors`` asks for the exception instead.
+    The file is read with ``weights_only=True`` (tensors, containers, numbers, strings: all the reference's schema needs);
+    ``trust_pickle=True`` allows the full unpickler for checkpoints from a trusted source that carry other objects."""
     dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
     try:
         if not os.path.exists(path):
             raise FileNotFoundError(path)
-        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        ckpt = _load_checkpoint_file(path, trust_pickle)
         sd = _pick_state_dict(ckpt)
         if sd is None:
             raise KeyError("no state dict in checkpoint")
@@ -76,11 +87,16 @@ def load_denoising_model(path: str, fallback_config: Optional[Mapping] = None, d
 
 def save_checkpoint(name: str, model: GRUUNet2, optimizer=None, scheduler=None, arch: Optional[str] = None, last_epoch=None,
                     loss_record=None, loss_metric=None, total_training_iters=None, last_target_name=None, last_batch_size=None,
-                    tag: str = "uuid", allow_overwrite: bool = False, prefix: str = "saves") -> str:
-    """Write ``<prefix>/<name>-<tag>/checkpoint.pth`` with the key set of ``save_model`` (server.py:55-84); returns the path."""
-    if tag == "uuid":
+                    tag: Optional[str] = None, allow_overwrite: bool = False, prefix: str = "saves", tag_uuid: bool = True,
+                    or_tag_date: bool = True, last_dataset_name=None) -> str:
+    """Write ``<prefix>/<name>-<tag>/checkpoint.pth`` with the key set of ``save_model`` (server.py:36-84); returns the path.
+    Accepts the reference's keywords (``tag_uuid`` / ``or_tag_date`` / ``last_dataset_name``); ``tag="uuid" | "date" | "none"``
+    is a shorthand that overrides the two booleans.  (Like the reference, ``last_dataset_name`` is accepted and not stored.)"""
+    if tag is not None:
+        tag_uuid, or_tag_date = tag == "uuid", tag == "date"
+    if tag_uuid:
         name = f"{name}-{uuid.uuid4().hex[:6]}"
-    elif tag == "date":
+    elif or_tag_date:
         name = f"{name}-{datetime.datetime.now().strftime('%y%m%d')}"
     folder = os.path.join(prefix, name)
     if os.path.exists(folder) and not allow_overwrite:
@@ -122,7 +138,10 @@ class TrainingContext:
         return self.inner(*args, **kwargs)
 
     def __getattr__(self, item):
-        return getattr(self.__dict__["inner"], item)
+        inner = self.__dict__.get("inner")
+        if inner is None:  # copy / pickle probe the instance before __init__ ran
+            raise AttributeError(item)
+        return getattr(inner, item)
 
     def save(self, prefix: str = "saves") -> str:
         return save_checkpoint(self.name, self.inner, optimizer=self.optim, scheduler=self.sched,
@@ -131,8 +150,9 @@ class TrainingContext:
                                loss_metric={"train": "MSE", "test": "MAE"}, prefix=prefix)
 
     @classmethod
-    def load(cls, name: str, class_=GRUUNet2, prefix: str = "saves", training: bool = False, device: Optional[torch.device] = None):
-        ckpt = torch.load(os.path.join(prefix, name, "checkpoint.pth"), map_location="cpu", weights_only=False)
+    def load(cls, name: str, class_=GRUUNet2, prefix: str = "saves", training: bool = False, device: Optional[torch.device] = None,
+             trust_pickle: bool = False):
+        ckpt = _load_checkpoint_file(os.path.join(prefix, name, "checkpoint.pth"), trust_pickle)
         self = cls(class_, device=device, **ckpt["config"])
         self.inner.load_state_dict(ckpt["model_state_dict"])
         if ckpt.get("optimizer_state_dict") is not None:

@@ -99,6 +99,7 @@ class GRUUNet2(nn.Module):
         self.cell = _Cell(in_size, hidden_sizes, kernel_sizes, strides, paddings, num_gaussians)
         self.conv_mode = "mma"  # one of CONV_MODES
         self.exact_gates = False  # attribution switch: GRU gates through expf / IEEE division (B2D_CONV_EXACT_GATES)
+        self._cell_runner = None  # generic cell kernels for configurations other than the shipped one (csrc/cell.cu)
         self._native = {}  # device index -> NativeModel
         self._native_lock = threading.Lock()
         self._generation = 0  # bumped by repack()
@@ -120,6 +121,15 @@ class GRUUNet2(nn.Module):
         for k, s, p in zip(reversed(list(hp["kernel_sizes"])), reversed(list(hp["strides"])), reversed(list(hp["paddings"]))):
             n = (n - 1) * s - 2 * p + k + (s - 1 if s > 1 else 0)  # + s - 1: the largest length that still maps to n (64 -> 32)
         return n
+
+    def uses_tuned_kernels(self) -> bool:
+        """True for the shipped configuration (hidden 17 x 4 levels, 4 bins, k3 s2 p1, 2-16 Gaussians): the tensor-core /
+        register-resident kernels of csrc/model.cu + unet_mma.cu.  Every other configuration runs on the generic cell
+        kernels (csrc/cell.cu), same results contract, no fused chain."""
+        hp = self.hparams
+        return (list(hp["hidden_sizes"]) == [17, 17, 17, 17] and hp["num_compressed_bins"] == 4 and set(hp["kernel_sizes"]) == {3}
+                and set(hp["strides"]) == {2} and set(hp["paddings"]) == {1} and len(hp["kernel_sizes"]) == 4
+                and 2 <= hp["num_gaussians"] <= 16)
 
     # ---- native model management -------------------------------------------------------------
     def _signature(self):
@@ -182,7 +192,7 @@ class GRUUNet2(nn.Module):
             raise Exception(f"unknown!! {input.shape}")
         x = require_cuda_f32(input, "input")
         B, T, nm = x.shape
-        if nm != self.n_mels:
+        if self.uses_tuned_kernels() and nm != self.n_mels:
             raise ValueError(f"GRUUNet2 expects {self.n_mels} mel bins on the last axis, got {nm}")
         if hx is None:
             h = torch.zeros(B, self.latent_size, self.num_compressed_bins, dtype=x.dtype, device=x.device)
@@ -190,6 +200,13 @@ class GRUUNet2(nn.Module):
             h = require_cuda_f32(hx, "hx").clone()  # the reference never mutates the caller's hx
             if tuple(h.shape) != (B, self.latent_size, self.num_compressed_bins):
                 raise ValueError(f"hx must be [{B}, {self.latent_size}, {self.num_compressed_bins}], got {tuple(h.shape)}")
+        if not self.uses_tuned_kernels():
+            if self._cell_runner is None:
+                from ._cell import ARCH_GRUUNET2, CellRunner
+
+                self._cell_runner = CellRunner(self, ARCH_GRUUNET2)
+            out = self._cell_runner.forward(x, h)
+            return (out.squeeze(0) if two_dimmed else out), h
         out = torch.empty_like(x)
         if T == 0:
             return (out.squeeze(0) if two_dimmed else out), h

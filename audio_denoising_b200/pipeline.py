@@ -34,6 +34,9 @@ class DenoisePipeline:
                  n_iter: int = 32, momentum: float = 0.99, device: Optional[torch.device] = None, plan_flags: int = 0):
         if not isinstance(model, GRUUNet2):
             raise TypeError("model must be an audio_denoising_b200.GRUUNet2")
+        if not model.uses_tuned_kernels():
+            raise NotImplementedError("DenoisePipeline fuses the shipped GRUUNet2 configuration (hidden 17 x 4, 4 bins, k3 s2 p1); "
+                                      "other configurations run through model(x) and the transform modules")
         if n_mels != model.n_mels:
             raise ValueError(f"n_mels={n_mels} does not match the model ({model.n_mels})")
         if hop_length * 2 != n_fft:

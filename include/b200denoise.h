@@ -101,6 +101,33 @@ int b2d_model_create(const b2d_model_config* cfg, const float* const* h_params, 
 void b2d_model_destroy(b2d_model* model);
 int b2d_model_n_mels(const b2d_model* model); /* num_compressed_bins << levels */
 
+/* ---- the same cell for ANY configuration, and its sibling MOMO3 ---------------
+ * b2d_model above is the tuned engine of the shipped GRUUNet2 configuration.  b2d_cell runs the reference's conv-GRU U-Net
+ * cell generically (fp32 FMA kernels, same three phases): per-level hidden sizes, kernel sizes, strides, paddings, any
+ * n_mels that compresses to num_compressed_bins (odd lengths, padding 0).
+ *   B2D_ARCH_GRUUNET2  gruunet2.py:71-306 (and gruunet.py: the same maths)
+ *   B2D_ARCH_MOMO3     momo3.py:191-324: input channels (x_t, x_t - x_{t-1}), Gaussian channels at the encoder input only
+ * h_params: state_dict parameters() order as for b2d_model_create; h_gs_offsets: input, reset (and output for GRUUNET2) gate.
+ * b2d_cell_forward: x [B, T, n_mels], prev [B, n_mels] or NULL (MOMO3: the frame before x[:, 0]; NULL = x[:, 0] itself,
+ * momo3.py:277-278), hx [B, hidden[-1], bins] in/out, out [B, T, n_mels]. */
+#define B2D_ARCH_GRUUNET2 0
+#define B2D_ARCH_MOMO3 1
+typedef struct b2d_cell b2d_cell;
+typedef struct {
+  int arch;
+  int num_compressed_bins;
+  int levels;
+  int num_gaussians;
+  int n_mels;
+  int hidden[8], kernel[8], stride[8], padding[8];
+} b2d_cell_config;
+int b2d_cell_create(const b2d_cell_config* cfg, const float* const* h_params, int n_params,
+                    const float* const* h_gs_offsets, b2d_cell** out);
+void b2d_cell_destroy(b2d_cell* cell);
+size_t b2d_cell_workspace_bytes(const b2d_cell* cell, int B, int T);
+int b2d_cell_forward(const b2d_cell* cell, const float* x, const float* prev, float* hx, float* out, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K0: per-clip peak (app3.py:181-186) ------------------------------------------------------
  * peak[b] = max|wave[b,:]| if > 1e-6 else 1. */
 int b2d_peak(const float* wave, int B, int L, float* peak, void* stream);

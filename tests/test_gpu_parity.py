@@ -944,3 +944,87 @@ def test_exact_math_attribution(dev, golden):
     for name, row in table.items():
         assert min(row["default"]) >= 40.0, (name, row["default"])
         assert min(row["all_exact"]) >= 40.0, (name, row["all_exact"])
+
+
+# ---------------------------------------------------------------------------------------------- sibling models
+@pytest.mark.parametrize("nm", [24, 27])
+def test_momo3_matches_reference_golden(dev, golden, nm):
+    """momo3.MOMO3 with the shipped MOMO3-4d4ea0 weights (hidden (16,16,16), paddings (1,0,1), delta-feature input) on the
+    generic cell kernels against outputs of the reference module itself: full sequence, given hx, 2-D input, and chunked
+    calls with hx / prev carried (momo3.py:272-324)."""
+    import audio_denoising_b200 as adb
+
+    _, metrics, *_ = _oracle()
+    sd, cfg = load_weights("momo3")
+    m = adb.MOMO3(**cfg)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    s = golden("siblings.npz")
+    x = torch.from_numpy(s[f"momo_{nm}_x"]).to(dev)
+    y, h = m(x)
+    assert metrics.rel_l2(y.cpu(), torch.from_numpy(s[f"momo_{nm}_y"])) < 1e-5
+    assert metrics.rel_l2(h.cpu(), torch.from_numpy(s[f"momo_{nm}_h"])) < 1e-5
+    h0 = torch.from_numpy(s[f"momo_{nm}_h0"]).to(dev)
+    y2, h2 = m(x, h0)
+    assert metrics.rel_l2(y2.cpu(), torch.from_numpy(s[f"momo_{nm}_y_h0"])) < 1e-5
+    assert metrics.rel_l2(h2.cpu(), torch.from_numpy(s[f"momo_{nm}_h_h0"])) < 1e-5
+    assert torch.equal(h0.cpu(), torch.from_numpy(s[f"momo_{nm}_h0"]))  # the caller's hx is not mutated
+    ya, ha = m(x[:, :4])
+    yb, hb = m(x[:, 4:], ha, prev=x[:, 3:4])
+    assert torch.equal(torch.cat([ya, yb], 1), y) and torch.equal(hb, h)  # chunked carry is bit-identical
+    y2d, h2d = m(x[0])
+    assert y2d.shape == (9, nm)
+    assert metrics.rel_l2(y2d.cpu(), torch.from_numpy(s[f"momo_{nm}_y2d"])) < 1e-5
+    with pytest.raises(_cabi_error()):
+        m(torch.zeros(1, 3, 40, device=dev))  # 40 bins do not compress to the model's 3
+
+
+def _cabi_error():
+    from audio_denoising_b200 import _cabi
+
+    return _cabi.B2DError
+
+
+def test_gruunet_generic_configuration_matches_reference_golden(dev, golden):
+    """gruunet.GRUUNet (gruunet.py: the same cell as gruunet2) in a configuration the tuned kernels do not cover -- hidden
+    (8, 12), kernels (3, 5), paddings (1, 2), 5 bins, 4 Gaussians -- against the reference module's own output."""
+    import audio_denoising_b200 as adb
+
+    _, metrics, *_ = _oracle()
+    s = golden("siblings.npz")
+    cfg = json.loads(bytes(s["gru_cfg"]).decode())
+    m = adb.GRUUNet(**cfg)
+    assert not m.uses_tuned_kernels()
+    sd = {k[len("gru_sd__"):]: torch.from_numpy(s[k]) for k in s.files if k.startswith("gru_sd__")}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    y, h = m(torch.from_numpy(s["gru_x"]).to(dev))
+    assert metrics.rel_l2(y.cpu(), torch.from_numpy(s["gru_y"])) < 1e-5
+    assert metrics.rel_l2(h.cpu(), torch.from_numpy(s["gru_h"])) < 1e-5
+    with pytest.raises(NotImplementedError):
+        adb.DenoisePipeline(m, n_fft=1024, hop_length=512, n_mels=20, sample_rate=16000)
+
+
+@pytest.mark.parametrize("name", CHECKPOINTS)
+def test_gruunet_class_loads_gruunet2_checkpoints(dev, golden, name):
+    """A checkpoint written for GRUUNet2 loads through the GRUUNet class (identical state_dict layout, gruunet.py:246-300) and
+    reproduces the reference outputs on the tuned kernels; on the generic cell kernels the same weights agree to 1e-5."""
+    import audio_denoising_b200 as adb
+    from audio_denoising_b200._cell import ARCH_GRUUNET2, CellRunner
+
+    _, metrics, *_ = _oracle()
+    sd, cfg = load_weights(name)
+    m = adb.GRUUNet(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    io = golden("model_io.npz")
+    x = torch.from_numpy(io["x"]).to(dev)
+    y, h = m(x)
+    assert metrics.rel_l2(y.cpu(), torch.from_numpy(io[f"{name}_y"])) < 1e-5
+    assert metrics.rel_l2(h.cpu(), torch.from_numpy(io[f"{name}_h"])) < 1e-5
+    hg = torch.zeros_like(h)
+    yg = CellRunner(m, ARCH_GRUUNET2).forward(x, hg)
+    assert metrics.rel_l2(yg.cpu(), torch.from_numpy(io[f"{name}_y"])) < 1e-5
+    assert metrics.rel_l2(hg.cpu(), torch.from_numpy(io[f"{name}_h"])) < 1e-5

@@ -219,3 +219,22 @@ def test_resample_and_ingest_refuse_cpu_tensors():
         adb.pcm16_to_float(torch.zeros(10, dtype=torch.int16))
     with pytest.raises(NotImplementedError):
         adb.Resample(44100, 48000, resampling_method="sinc_interp_kaiser")
+
+
+def test_momo3_dropin_state_dict_and_interface():
+    """momo3.MOMO3 drop-in: constructor, state_dict keys / shapes / order of the shipped MOMO3-4d4ea0 checkpoint, hparams helpers;
+    CPU tensors are refused (no fallback)."""
+    import audio_denoising_b200 as adb
+    from conftest import load_weights
+
+    sd, cfg = load_weights("momo3")
+    m = adb.MOMO3(**cfg)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [tuple(v.shape) for v in sd.values()]
+    m.load_state_dict(sd)
+    assert m.get_config() == m.hparams and adb.MOMO3.from_config(m.get_config()).latent_size == 16
+    assert m.num_compressed_bins == 3
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 24))
+    g = adb.GRUUNet2(4, 1, (8, 12), (3, 5), (2, 2), (1, 2))
+    assert not g.uses_tuned_kernels() and adb.GRUUNet2(4, 1, (17,) * 4, (3,) * 4, (2,) * 4, (1,) * 4).uses_tuned_kernels()
