@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200denoise.so")
-SOURCES = ["api.cu", "dsp.cu", "griffinlim.cu", "gl_fast.cu", "gl_fast_n512.cu", "gl_fast_n2048.cu", "gl_warp.cu", "gl_reg.cu", "model.cu", "cell.cu", "conv_tc.cu", "unet_mma.cu", "stream.cu", "ingest.cu"]
+SOURCES = ["api.cu", "dsp.cu", "griffinlim.cu", "gl_fast.cu", "gl_fast_n512.cu", "gl_fast_n2048.cu", "gl_warp.cu", "gl_reg.cu", "model.cu", "cell.cu", "invmel_tc.cu", "unet_mma.cu", "unet_tc.cu", "stream.cu", "ingest.cu"]
 
 
 def _newest_source_mtime() -> float:

@@ -27,7 +27,7 @@ int fail(int code, const char* fmt, ...) {
 
 int model_pack(b2d_model* m, const float* const* hp, const float* const* offs);  // model.cu
 bool model_config_supported(const b2d_model_config* c);
-int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv);  // conv_tc.cu
+int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv);  // invmel_tc.cu
 int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);
 int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, int S, float* hx, float* ola,
                      const float2* init_angles, unsigned long long seed, const unsigned long long* d_seed, int n_iter, float momentum,
@@ -207,8 +207,8 @@ int b2d_model_create(const b2d_model_config* cfg, const float* const* h_params, 
 void b2d_model_destroy(b2d_model* m) {
   if (!m) return;
   cudaFree(m->d_blob);
-  cudaFree(m->d_tc);
   cudaFree(m->d_mma);
+  cudaFree(m->d_utc);
   free(m->h_blob);
   delete m;
 }

@@ -89,7 +89,7 @@ struct b2d_plan {
   int* d_seg_first;   // [n_mels + 1] first segment of each mel column
   int mel_seg_pad;    // number of segments rounded up to a multiple of 32
   float* d_pinv;      // [Fp, n_mels] rows F..Fp-1 zero
-  float2* d_tw8;      // TF32 big/small weight images of pinv for the tcgen05 inverse-mel GEMM (conv_tc.cu), may be null
+  float2* d_tw8;      // TF32 big/small weight images of pinv for the tcgen05 inverse-mel GEMM (invmel_tc.cu), may be null
 };
 
 struct b2d_model {
@@ -103,9 +103,6 @@ struct b2d_model {
   int enc_w[6], enc_pb[6];
   int rec_w, rec_pb;
   int dec_w[6], dec_pb[6];
-  // bf16 operand images for the tcgen05 path (hi / lo split), see conv_tc.cu
   float* d_mma;       // weight fragment images for the warp-level MMA decoder (unet_mma.cu)
-  void* d_tc;
-  size_t tc_bytes;
-  int tc_off[32];
+  float* d_utc;       // weight images of the fused tcgen05 encoder (unet_tc.cu)
 };

@@ -7,8 +7,8 @@
 //
 // The GaussianSmearing position channels (gruunet2.py:54-68) are input independent, so their
 // contribution is folded into a per-position bias when the model is packed.
-// This file holds the fp32 CUDA-core convolutions (conv_mode 0, the parity mode); conv_tc.cu holds
-// the tcgen05 implicit-GEMM variants of the encoder / decoder.
+// This file holds the fp32 CUDA-core convolutions (B2D_CONV_FP32, the exact engine) and the recurrence; unet_mma.cu holds the
+// default warp-level tensor-core encoder / decoder, unet_tc.cu the fused tcgen05 encoder.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -394,8 +394,10 @@ static void smear_table(const float* off, int G, int nbins, std::vector<double>&
   }
 }
 
-int model_pack_tc_weights(b2d_model* m, const float* const* hp);  // conv_tc.cu
 int model_pack_mma(b2d_model* m);                                    // unet_mma.cu
+int model_pack_utc(b2d_model* m, const float* const* hp);             // unet_tc.cu
+int model_encode_utc(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx, int num_sms,
+                     cudaStream_t st);
 int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx, int terms,
                      int num_sms, cudaStream_t st);
 int model_decode_mma(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
@@ -488,15 +490,7 @@ int model_pack(b2d_model* m, const float* const* hp, const float* const* offs) {
   B2D_CUDA(cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   int rc = model_pack_mma(m);  // weight fragments for the warp-level MMA decoder (unet_mma.cu)
   if (rc != B2D_OK) return rc;
-  return model_pack_tc_weights(m, hp);  // TF32 big/small weight images for the tcgen05 path (conv_tc.cu)
-}
-
-struct PackedOffsets { int enc_pb[4]; int dec_pb[4]; };
-PackedOffsets packed_offsets() {
-  const Packed L = packed_layout();
-  PackedOffsets o;
-  for (int i = 0; i < 4; ++i) { o.enc_pb[i] = L.enc_pb[i]; o.dec_pb[i] = L.dec_pb[i]; }
-  return o;
+  return model_pack_utc(m, hp);  // weight images of the fused tcgen05 encoder (unet_tc.cu)
 }
 
 bool model_config_supported(const b2d_model_config* c) {
@@ -504,60 +498,52 @@ bool model_config_supported(const b2d_model_config* c) {
          c->padding == 1 && c->num_gaussians >= 2 && c->num_gaussians <= 16;
 }
 
-// workspace: d0 | d1 | d2 | gx | hseq | decoder scratch u0,u1,u2 (tensor-core path)
+// workspace: d0 | d1 | d2 | gx | hseq
 size_t model_workspace_bytes(const b2d_model* m, int B, int T) {
   (void)m;
   const size_t nf = (size_t)B * T;
   return align_up(nf * D0 * 4, 256) + align_up(nf * D1 * 4, 256) + align_up(nf * D2 * 4, 256) + align_up(nf * GX * 4, 256) +
-         align_up(nf * HS * 4, 256) + align_up(nf * (size_t)H * (8 + 16 + 32) * 4, 256);
+         align_up(nf * HS * 4, 256);
 }
 
-int model_forward_tc(const b2d_model* m, const float* x, size_t nframes, float* d0, float* d1, float* d2, float* gx,
-                     int conv_mode, cudaStream_t st);  // conv_tc.cu
-int model_decode_tc(const b2d_model* m, const float* hseq, const float* d0, const float* d1, const float* d2, const float* x,
-                    size_t nframes, float* pred, float* mel, int fused_mode, float out_scale, int conv_mode, float* scratch,
-                    cudaStream_t st);
-
+// conv_mode (low byte): B2D_CONV_FP32 = fp32 FMA kernels of this file (the exact reference engine), B2D_CONV_MMA = warp-level
+// tensor-core MMAs with the fp32-class TF32 split (unet_mma.cu; the default: fastest), B2D_CONV_UTC = the fused tcgen05 / TMEM
+// encoder (unet_tc.cu) + the warp-MMA decoder.
 int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, float* mel_bt, int fused_mode,
                   float out_scale, int B, int T, int conv_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   B2D_REQUIRE(B >= 1 && T >= 1, B2D_ERR_BAD_ARG, "GRUUNet2 forward needs B >= 1 and T >= 1 (got %d, %d)", B, T);
   B2D_REQUIRE(ws != nullptr && ws_bytes >= model_workspace_bytes(m, B, T), B2D_ERR_WORKSPACE, "GRUUNet2 workspace too small");
   const bool exact_gates = (conv_mode & B2D_CONV_EXACT_GATES) != 0;
   conv_mode &= 0xff;
-  B2D_REQUIRE(conv_mode >= 0 && conv_mode <= 4, B2D_ERR_BAD_ARG, "conv_mode must be in [0, 4]");
-  const bool fma_encoder = (conv_mode == 0);
+  B2D_REQUIRE(conv_mode == B2D_CONV_FP32 || conv_mode == B2D_CONV_MMA || conv_mode == B2D_CONV_UTC, B2D_ERR_BAD_ARG,
+              "conv_mode must be B2D_CONV_FP32 (0), B2D_CONV_MMA (3) or B2D_CONV_UTC (5), got %d", conv_mode);
   const size_t nf = (size_t)B * T;
   unsigned char* base = static_cast<unsigned char*>(ws);
   float* d0 = reinterpret_cast<float*>(base); base += align_up(nf * D0 * 4, 256);
   float* d1 = reinterpret_cast<float*>(base); base += align_up(nf * D1 * 4, 256);
   float* d2 = reinterpret_cast<float*>(base); base += align_up(nf * D2 * 4, 256);
   float* gx = reinterpret_cast<float*>(base); base += align_up(nf * GX * 4, 256);
-  float* hseq = reinterpret_cast<float*>(base); base += align_up(nf * HS * 4, 256);
-  float* dec_scratch = reinterpret_cast<float*>(base);
+  float* hseq = reinterpret_cast<float*>(base);
   const Packed L = packed_layout();
   int dev_sms = 148;
   if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess || dev_sms < 1) dev_sms = 148;
-  if (fma_encoder) {
+  int rc;
+  if (conv_mode == B2D_CONV_FP32) {
     const size_t smem = sizeof(float) * (size_t)(((L.rec_w + 3) & ~3) + ENC_WARPS * ENC_ACT);
     B2D_SMEM_OPT_IN(smem, encoder_kernel);
     const size_t want = (nf + ENC_WARPS - 1) / ENC_WARPS;
     const int grid = (int)(want < (size_t)dev_sms * 3 ? want : (size_t)dev_sms * 3);
     encoder_kernel<<<grid, ENC_WARPS * 32, smem, st>>>(m->d_blob, x, nf, d0, d1, d2, gx);
     B2D_LAUNCH_CHECK("encoder_kernel");
-  } else if (conv_mode >= 3) {
-    int rc = model_encode_mma(m, x, nf, d0, d1, d2, gx, conv_mode == 3 ? 3 : 1, dev_sms, st);
-    if (rc != B2D_OK) return rc;
+  } else if (conv_mode == B2D_CONV_UTC) {
+    if ((rc = model_encode_utc(m, x, nf, d0, d1, d2, gx, dev_sms, st))) return rc;
   } else {
-    int rc = model_forward_tc(m, x, nf, d0, d1, d2, gx, conv_mode, st);
-    if (rc != B2D_OK) return rc;
+    if ((rc = model_encode_mma(m, x, nf, d0, d1, d2, gx, 3, dev_sms, st))) return rc;
   }
   if (exact_gates) recurrence_kernel<true><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
   else recurrence_kernel<false><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
   B2D_LAUNCH_CHECK("recurrence_kernel");
-  if (conv_mode >= 3) {
-    int rc = model_decode_mma(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode == 3 ? 3 : 1, dev_sms, st);
-    if (rc != B2D_OK) return rc;
-  } else if (conv_mode == 0) {
+  if (conv_mode == B2D_CONV_FP32) {
     const int nw = L.total - L.dec_w[0];
     const size_t smem = sizeof(float) * (size_t)(((nw + 3) & ~3) + DEC2_WARPS * DEC2_FW * DEC2_FR);
     B2D_SMEM_OPT_IN(smem, decoder2_kernel);
@@ -566,8 +552,7 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
     decoder2_kernel<<<grid, DEC2_WARPS * 32, smem, st>>>(m->d_blob, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale);
     B2D_LAUNCH_CHECK("decoder2_kernel");
   } else {
-    int rc = model_decode_tc(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, conv_mode, dec_scratch, st);
-    if (rc != B2D_OK) return rc;
+    if ((rc = model_decode_mma(m, hseq, d0, d1, d2, x, nf, pred, mel_bt, fused_mode, out_scale, 3, dev_sms, st))) return rc;
   }
   return B2D_OK;
 }

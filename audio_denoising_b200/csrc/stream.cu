@@ -8,7 +8,7 @@
 
 namespace b2d {
 
-int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);  // conv_tc.cu
+int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st);  // invmel_tc.cu
 
 // workspace: peak[S] | x[S,N] | logmel[S,3,M] | pred | mel | mag[S,3,Fp] | y[S,N] | model ws | GL ws
 struct StreamWs {

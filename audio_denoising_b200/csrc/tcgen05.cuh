@@ -29,6 +29,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the accumulate flag as an immediate predicate (no setp per instruction in the single issuing thread)
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_imm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if (ACC) {
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc),
+                 "l"(b_desc), "r"(idesc)
+                 : "memory");
+  } else {
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc),
+                 "l"(b_desc), "r"(idesc)
+                 : "memory");
+  }
+}
 // the mbarrier gets one arrival when every tcgen05.mma this thread issued so far has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_addr(bar)) : "memory");
@@ -46,10 +59,11 @@ __device__ __forceinline__ void ld16(uint32_t taddr, float* v) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the loaded registers may be used after this (one wait covers every tcgen05.ld issued before it)
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // canonical K-major no-swizzle layout (TF32: 4 elements per 16-byte core-matrix row):

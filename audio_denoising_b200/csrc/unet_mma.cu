@@ -1,19 +1,21 @@
 // unet_mma.cu -- GRUUNet2 decoder (output_gate UpBlocks, gruunet2.py:184-199) on warp-level tensor-core MMAs.
 //
-// Why warp-level mma.sync and not tcgen05 here: the U-Net has 17 channels.  One ConvTranspose1d(k3, s2, p1, op1) is
+// Why warp-level mma.sync is the default engine and not tcgen05: the U-Net has 17 channels.  One ConvTranspose1d(k3, s2, p1, op1) is
 //   out[2i]   = pb + x[i] W1,      out[2i+1] = pb + x[i] W2 + x[i+1] W0        (x[i]: the Cin-vector at input position i)
-// i.e. per frame a [Lin x Cin] x [Cin x 17] GEMM with Lin = 4..32 rows.  tcgen05 needs 128-row operand tiles staged in
-// shared memory in core-matrix layout plus a TMEM round trip per layer (conv_tc.cu does exactly that and is 10x slower than
-// this file: the staging, not the MMA, is the cost); a warp-level m16n8k8 MMA takes its operands straight from registers,
-// so a warp keeps two frames' activations in its own shared-memory rows ([position][channel], stride 44 floats:
-// conflict-free fragment loads) and walks the four layers without leaving the SM.  Measured on B200: 919 m16n8k8 TF32
-// MMAs / us / SM (tools/micro/mma_rate.cu), 3.9x the FP32 FMA peak -- and, more to the point, one shared-memory operand
-// fetch feeds 1024 MACs instead of 128.
+// i.e. per frame a [Lin x Cin] x [Cin x 17] GEMM with Lin = 4..32 rows.  tcgen05 needs 128-row operand tiles staged in shared
+// memory in core-matrix layout and a TMEM round trip per layer.  The fair trial of that design is unet_tc.cu: all encoder
+// layers fused in one persistent kernel, activations written from the epilogue straight into the next layer's operand, weights
+// by TMA, two tile slots per SM -- correct to 4e-6 and 120-130 us against this file's 98 us (tensor pipe 17 % busy, issue slots
+// 17 %: the time goes into the per-layer hand-offs, fence -> barrier -> one thread issuing 24 MMAs -> commit -> mbarrier ->
+// tcgen05.ld, of which only two run per SM at a time because a tile slot's A operand with its big + small planes takes 64 KB).
+// A warp-level m16n8k8 MMA takes its operands straight from registers, so a warp keeps two frames' activations in its own
+// shared-memory rows ([position][channel], stride 44 floats: conflict-free fragment loads) and walks the four layers without
+// leaving the SM or waiting for any other warp.  Measured on B200: 919 m16n8k8 TF32 MMAs / us / SM (tools/micro/mma_rate.cu),
+// 3.9x the FP32 FMA peak -- and, more to the point, one shared-memory operand fetch feeds 1024 MACs instead of 128.
 //
 // Precision: every operand is split into TF32 big + small parts (big = round-to-nearest TF32, small = exact remainder)
 // and three MMAs are issued per tile (big*big + small*big + big*small), fp32 accumulate: fp32-class results (model parity
-// < 1e-5, same as the FMA kernels).  conv_mode 4 issues the big*big term only (TF32 = 10-bit mantissa, still above the
-// bf16 the benchmark configuration names).
+// < 1e-5, same as the FMA kernels).
 //
 // Weight fragments are laid out at model-pack time exactly as the B operand registers want them:
 //   float4 (b0_big, b1_big, b0_small, b1_small) per lane per (layer, operand set, k-step, n-tile).
@@ -541,13 +543,9 @@ int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* 
   const size_t want = (nframes + EWARPS * G - 1) / (EWARPS * G);
   const int grid = (int)(want < (size_t)num_sms ? want : (size_t)num_sms);
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma) + (size_t)dfrag_off(4) * 32;
-  if (terms == 3) {
-    B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<3>);
-    encoder_mma_kernel<3><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
-  } else {
-    B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<1>);
-    encoder_mma_kernel<1><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
-  }
+  (void)terms;  // always the fp32-class 3 x TF32 split
+  B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<3>);
+  encoder_mma_kernel<3><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
   B2D_LAUNCH_CHECK("encoder_mma_kernel");
   return B2D_OK;
 }
@@ -560,13 +558,9 @@ int model_decode_mma(const b2d_model* m, const float* hseq, const float* d0, con
   const size_t want = (nframes + WARPS * G - 1) / (WARPS * G);
   const int grid = (int)(want < (size_t)num_sms ? want : (size_t)num_sms);
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma);
-  if (terms == 3) {
-    B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<3>);
-    decoder_mma_kernel<3><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
-  } else {
-    B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<1>);
-    decoder_mma_kernel<1><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
-  }
+  (void)terms;
+  B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<3>);
+  decoder_mma_kernel<3><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
   B2D_LAUNCH_CHECK("decoder_mma_kernel");
   return B2D_OK;
 }

@@ -25,10 +25,10 @@ from torch import nn
 from . import _cabi
 from ._runtime import require_cuda_f32, stream_ptr
 
-# "fp32": CUDA-core FMA convolutions; "tf32x3": tcgen05 implicit GEMM, operands split into big+small TF32 parts (3 MMAs,
-# fp32-class accuracy); "tf32": tcgen05 single pass (11-bit mantissa operands, fp32 accumulate); "mma": warp-level m16n8k8
-# tensor-core MMAs with the same big+small split (fp32-class) for the decoder; "mma_tf32": the same, single pass
-CONV_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2, "mma": 3, "mma_tf32": 4}
+# convolution engines (include/b200denoise.h B2D_CONV_*): "mma" = warp-level TF32 tensor-core MMAs with the fp32-class big + small
+# split (default, fastest); "utc" = the encoder as one persistent tcgen05 / TMEM kernel + the warp-MMA decoder; "fp32" = CUDA-core
+# FMA kernels (the exact engine of the attribution test)
+CONV_MODES = {"fp32": 0, "mma": 3, "utc": 5}
 
 
 class _PositionCode(nn.Module):

@@ -149,11 +149,17 @@ int b2d_mel_scale(const b2d_plan* plan, const float* mag, int B, int T, float* m
 /* ---- K3: GRUUNet2.forward (gruunet2.py:290-306) -----------------------------------------------
  * x [B, T, n_mels], hx [B, hidden, bins] in/out (caller zero-fills it for hx=None), out [B, T, n_mels].
  * Runs encoder (time-parallel) -> persistent recurrence -> decoder (time-parallel).
- * conv_mode (low byte): 0 = fp32 CUDA-core convolutions, 1 = tcgen05/TMEM implicit GEMM with TF32 operands split into
- * big + small parts (3 MMAs per k-step, fp32-class accuracy), 2 = tcgen05 single-pass TF32 (throughput mode),
- * 3 = decoder on warp-level m16n8k8 tensor-core MMAs with the same big + small split (fp32-class), 4 = the same, single pass.
+ * conv_mode (low byte) selects the convolution engine:
+ *   B2D_CONV_MMA   (default) encoder + decoder on warp-level m16n8k8 TF32 tensor-core MMAs, every operand split into big +
+ *                  small TF32 parts (3 MMAs per tile: fp32-class accuracy); the fastest engine for this 17-channel model;
+ *   B2D_CONV_UTC   the encoder as ONE persistent tcgen05 / TMEM kernel (implicit GEMMs chained through shared memory, weights by
+ *                  TMA, same 3 x TF32 split) + the warp-MMA decoder;
+ *   B2D_CONV_FP32  fp32 CUDA-core FMA kernels: the exact engine the attribution test compares the others with.
  * B2D_CONV_EXACT_GATES or-ed in: GRU gate sigmoid / tanh through expf and IEEE division instead of ex2.approx / rcp.approx
  * (the reference's torch.sigmoid / torch.tanh, gruunet2.py:231-240) -- the model's switch for test_exact_math_attribution. */
+#define B2D_CONV_FP32 0
+#define B2D_CONV_MMA 3
+#define B2D_CONV_UTC 5
 #define B2D_CONV_EXACT_GATES 0x100
 size_t b2d_gruunet2_workspace_bytes(const b2d_model* model, int B, int T);
 int b2d_gruunet2_forward(const b2d_model* model, const float* x, float* hx, float* out, int B, int T,

@@ -14,7 +14,7 @@ m.load_state_dict(sd)
 m = m.to(dev)
 x = torch.rand(B, T, 64, device=dev) * 3
 ref = None
-modes = sys.argv[1:] or ["fp32", "mma", "mma_tf32"]
+modes = sys.argv[1:] or ["fp32", "mma", "utc"]
 for mode in modes:
     m.conv_mode = mode
     y, h = m(x); torch.cuda.synchronize()
