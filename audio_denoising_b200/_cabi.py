@@ -68,6 +68,9 @@ SIGNATURES = {
     "b2d_cell_destroy": (None, [_vp]),
     "b2d_cell_workspace_bytes": (_sz, [_vp, _i, _i]),
     "b2d_cell_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "b2d_cell_num_param_floats": (_i, [_vp]),
+    "b2d_cell_backward_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "b2d_cell_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "b2d_peak": (_i, [_vp, _i, _i, _vp, _vp]),
     "b2d_stft": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2d_stft_mel_log1p": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),

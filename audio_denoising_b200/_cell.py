@@ -64,6 +64,13 @@ class CellRunner:
             self._cells[(idx, n_mels)] = nc
             return nc
 
+    def forward_autograd(self, x: torch.Tensor, h0: torch.Tensor, prev: torch.Tensor | None = None):
+        """Differentiable forward: (out [B, T, n_mels], h_T [B, H, bins]) with gradients to x, h0 and every parameter of the
+        module, computed by the fp32 backward kernels of csrc/cell.cu (``b2d_cell_backward``)."""
+        module = self._module()
+        params = [p for p in module.parameters()]
+        return _CellFunction.apply(self, x, h0, prev, *params)
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor, h: torch.Tensor, prev: torch.Tensor | None = None):
         """x [B, T, n_mels], h [B, H, bins] (updated in place), prev [B, n_mels] or None -> out [B, T, n_mels]."""
@@ -80,3 +87,56 @@ class CellRunner:
             _cabi.check(lib.b2d_cell_forward(cell.handle, x.data_ptr(), ptr(prev), h.data_ptr(), out.data_ptr(), B, T,
                                              ws.data_ptr(), ws.numel(), stream_ptr(x.device)))
         return out
+
+
+class _CellFunction(torch.autograd.Function):
+    """autograd bridge: forward = b2d_cell_forward (its workspace is kept for the backward), backward = b2d_cell_backward."""
+
+    @staticmethod
+    def forward(ctx, runner: CellRunner, x, h0, prev, *params):
+        x = require_cuda_f32(x, "input")
+        h0 = require_cuda_f32(h0, "hx")
+        B, T, nm = x.shape
+        lib = _cabi.lib()
+        cell = runner.native(x.device, nm)
+        if prev is not None:
+            prev = require_cuda_f32(prev, "prev").reshape(B, nm)
+        h = h0.clone()
+        out = torch.empty_like(x)
+        ws = torch.empty(max(int(lib.b2d_cell_workspace_bytes(cell.handle, B, max(T, 1))), 256), dtype=torch.uint8, device=x.device)
+        if T > 0:
+            with torch.cuda.device(x.device):
+                _cabi.check(lib.b2d_cell_forward(cell.handle, x.data_ptr(), ptr(prev), h.data_ptr(), out.data_ptr(), B, T,
+                                                 ws.data_ptr(), ws.numel(), stream_ptr(x.device)))
+        ctx.cell, ctx.ws, ctx.prev = cell, ws, prev
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(x, h0)
+        ctx.mark_non_differentiable()
+        return out, h
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_h):
+        x, h0 = ctx.saved_tensors
+        B, T, nm = x.shape
+        lib = _cabi.lib()
+        cell = ctx.cell
+        n = lib.b2d_cell_num_param_floats(cell.handle)
+        gx = torch.zeros_like(x)
+        gh0 = torch.zeros_like(h0) if grad_h is None else grad_h.contiguous().clone()
+        gp = torch.zeros(n, dtype=torch.float32, device=x.device)
+        if T > 0:
+            go = (torch.zeros_like(x) if grad_out is None else grad_out.contiguous().float())
+            gh = None if grad_h is None else grad_h.contiguous().float()
+            ws = torch.empty(max(int(lib.b2d_cell_backward_workspace_bytes(cell.handle, B, T)), 256), dtype=torch.uint8, device=x.device)
+            with torch.cuda.device(x.device):
+                _cabi.check(lib.b2d_cell_backward(cell.handle, x.data_ptr(), ptr(ctx.prev), h0.data_ptr(), ctx.ws.data_ptr(), go.data_ptr(),
+                                                  ptr(gh), gx.data_ptr(), gh0.data_ptr(), gp.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
+                                                  stream_ptr(x.device)))
+        grads, o = [], 0
+        for shp in ctx.shapes:
+            k = 1
+            for v in shp:
+                k *= v
+            grads.append(gp[o:o + k].view(shp))
+            o += k
+        return (None, gx, gh0, None, *grads)

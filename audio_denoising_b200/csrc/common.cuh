@@ -52,6 +52,31 @@ extern std::atomic<unsigned long long> g_launches;
     }                                                                                                            \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Back-to-back launches of the same persistent kernel (32 Griffin-Lim iterations) pay launch latency + the table / twiddle
+// prologue + the drain of the slowest SM between every pair.  A kernel launched with launch_pdl() may start its CTAs as soon as
+// the CTAs of the kernel before it in the stream have exited (or called pdl_trigger()); everything it does before pdl_wait()
+// must touch only memory no earlier kernel of the chain writes (plan tables); pdl_wait() returns once the previous kernel has
+// completed and its writes are visible.  Launched without the attribute both calls are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

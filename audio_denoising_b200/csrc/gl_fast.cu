@@ -148,6 +148,9 @@ __global__ void __launch_bounds__(IT_WARPS * 32, 1) gl_fast512_kernel(const GlFa
   const float2 nmom = make_float2(-a.mom, -a.mom);
   constexpr uint32_t ring_bytes = (USE_PREV ? 2u : 1u) * HOP * 4u;
   uint32_t tma_uses = 0, xuse0 = 0, xuse1 = 0;  // completed phases of the three mbarriers (parity tracking across runs)
+  // everything above read plan tables only; the iterates (and, for the first iteration, the magnitudes) come from the kernel before
+  pdl_wait();
+  pdl_trigger();
 
 #pragma unroll 1
   for (int gw = gw0; gw < nruns; gw += gstep) {
@@ -342,6 +345,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
   float2 carry[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) carry[q] = make_float2(0.f, 0.f);
+  pdl_wait();  // magnitudes (and the seed) come from the kernels before
+  pdl_trigger();
   if (lane == 0) {
     mbar_expect_tx(bar, MAG_ROW_BYTES);
     bulk_g2s(mg_s, a.mag_tf + ((size_t)b * T + tb) * a.Fp, MAG_ROW_BYTES, bar);
@@ -405,7 +410,7 @@ int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, 
   constexpr int W = 8;
   const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
   B2D_SMEM_OPT_IN(smem, gl_fast512_init_kernel<W>);
-  gl_fast512_init_kernel<W><<<(B * R + W - 1) / W, W * 32, smem, st>>>(a);
+  B2D_CUDA(launch_pdl(gl_fast512_init_kernel<W>, dim3((B * R + W - 1) / W), dim3(W * 32), smem, st, a));
   B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
   return B2D_OK;
 }
@@ -476,6 +481,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 1) stft_fast512_kernel(const 
   const unsigned nframes = (unsigned)a.B * (unsigned)a.T;  // < 2^31 (checked by the launcher): 32-bit index math throughout
   const unsigned stride = gridDim.x * WARPS;
   const bool tma_ok = (a.L % 4) == 0;  // 16-byte aligned clip rows
+  pdl_wait();  // the waveform and the peaks come from the kernels before
+  pdl_trigger();
   // frame (b, t) is "interior" when its 1024 samples lie inside the clip: then it is one contiguous, aligned 4 KB read
   auto interior = [&](unsigned b, unsigned t, const float*& src) {
     const long s0 = (long)t * HOP - HOP;
@@ -594,7 +601,7 @@ int launch_stft_fast512(const b2d_plan* p, const float* wave, const float* inv_s
   const size_t nframes = (size_t)B * a.T;
   const size_t want = (nframes + W - 1) / W;
   const int grid = (int)(want < (size_t)p->num_sms ? want : (size_t)p->num_sms);
-  stft_fast512_kernel<<<grid, W * 32, smem, st>>>(a);
+  B2D_CUDA(launch_pdl(stft_fast512_kernel, dim3(grid), dim3(W * 32), smem, st, a));
   B2D_LAUNCH_CHECK("stft_fast512_kernel");
   return B2D_OK;
 }
@@ -606,7 +613,7 @@ static int launch_iteration(const GlFastArgs& a, int num_sms, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (256 + 256 + 512 + 512) + (size_t)IT_WARPS * IT_WARP_SMEM;
   B2D_SMEM_OPT_IN(smem, gl_fast512_kernel<USE_PREV, EXACT>);
   const int runs = a.B * a.R;
-  gl_fast512_kernel<USE_PREV, EXACT><<<runs < num_sms ? runs : num_sms, IT_WARPS * 32, smem, st>>>(a);
+  B2D_CUDA(launch_pdl(gl_fast512_kernel<USE_PREV, EXACT>, dim3(runs < num_sms ? runs : num_sms), dim3(IT_WARPS * 32), smem, st, a));
   B2D_LAUNCH_CHECK("gl_fast512_kernel");
   return B2D_OK;
 }

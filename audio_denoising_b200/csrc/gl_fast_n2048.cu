@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
   const size_t run_stride = (size_t)(n + 1) * HOP2;
   const int sub = 2 * odd;  // float offset of this warp's complex sample inside a float4 of the frame
   uint32_t uses = 0, xuse0 = 0, xuse1 = 0;
+  pdl_wait();  // the prologue above read plan tables only (common.cuh: programmatic dependent launch)
+  pdl_trigger();
 
 #pragma unroll 1
   for (int gp = gp0; gp < nruns; gp += gstep) {
@@ -331,7 +333,7 @@ static int launch_n2048(const GlN2048Args& a, int grid, cudaStream_t st) {
   using namespace n2048;
   const size_t smem = TABLE_BYTES + (size_t)PAIRS * PSMEM;
   B2D_SMEM_OPT_IN(smem, gl_fast_n2048_kernel<USE_PREV, INIT>);
-  gl_fast_n2048_kernel<USE_PREV, INIT><<<grid, PAIRS * 64, smem, st>>>(a);
+  B2D_CUDA(launch_pdl(gl_fast_n2048_kernel<USE_PREV, INIT>, dim3(grid), dim3(PAIRS * 64), smem, st, a));
   B2D_LAUNCH_CHECK("gl_fast_n2048_kernel");
   return B2D_OK;
 }

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(n512::WARPS * 32, 1) gl_fast_n512_kernel(const
   const int kU0 = lane, kU4 = lane - (lane == 0 ? 224 : 0);
   const size_t run_stride = (size_t)(n + 1) * HOPN;
   uint32_t uses = 0;
+  pdl_wait();  // the prologue above read plan tables only (common.cuh: programmatic dependent launch)
+  pdl_trigger();
 
 #pragma unroll 1
   for (int gw = gw0; gw < nruns; gw += gstep) {
@@ -272,10 +274,10 @@ int launch_gl_fast_n512(const b2d_plan* p, const float* mag_tf, float2* tprev, c
   const int grid = runs < p->num_sms ? runs : p->num_sms;
   if (use_prev) {
     B2D_SMEM_OPT_IN(smem, gl_fast_n512_kernel<true>);
-    gl_fast_n512_kernel<true><<<grid, WARPS * 32, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(gl_fast_n512_kernel<true>, dim3(grid), dim3(WARPS * 32), smem, st, a));
   } else {
     B2D_SMEM_OPT_IN(smem, gl_fast_n512_kernel<false>);
-    gl_fast_n512_kernel<false><<<grid, WARPS * 32, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(gl_fast_n512_kernel<false>, dim3(grid), dim3(WARPS * 32), smem, st, a));
   }
   B2D_LAUNCH_CHECK("gl_fast_n512_kernel");
   return B2D_OK;

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_kernel(const GlRegArgs a
   const float2 nmom = make_float2(-a.mom, -a.mom);
   constexpr uint32_t ring_bytes = (USE_PREV ? 2u : 1u) * HOP * 4u;
   uint32_t tma_uses = 0, xuse0 = 0, xuse1 = 0;
+  pdl_wait();  // the prologue above read plan tables only (common.cuh: programmatic dependent launch)
+  pdl_trigger();
 
 #pragma unroll 1
   for (int gw = gw0; gw < nruns; gw += gstep) {
@@ -300,7 +302,7 @@ static int launch_reg(const GlRegArgs& a, int num_sms, cudaStream_t st) {
   static_assert(RegSmem<R3>::TABLE_BYTES + W * RegSmem<R3>::WARP_BYTES <= 232448, "per-CTA shared memory exceeds 227 KB");
   B2D_SMEM_OPT_IN(smem, gl_reg_kernel<R3, W, MODE>);
   const int runs = a.B * a.R;
-  gl_reg_kernel<R3, W, MODE><<<runs < num_sms ? runs : num_sms, W * 32, smem, st>>>(a);
+  B2D_CUDA(launch_pdl(gl_reg_kernel<R3, W, MODE>, dim3(runs < num_sms ? runs : num_sms), dim3(W * 32), smem, st, a));
   B2D_LAUNCH_CHECK("gl_reg_kernel");
   return B2D_OK;
 }

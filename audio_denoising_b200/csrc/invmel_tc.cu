@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(128) invmel_tc_kernel(const TcInvMel L) {
   const size_t tiles = (L.nframes + 127) / 128;
   uint32_t mma_phase = 0;
   bool weights_ready = false;
+  pdl_wait();  // TMEM allocated, weight image in flight; mel comes from the decoder (common.cuh: programmatic dependent launch)
+  pdl_trigger();
   for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const size_t frame = tile * 128 + tid;
     const bool live = frame < L.nframes;
@@ -226,7 +228,7 @@ int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes
   const int ncols = (p->Fp + IM_N - 1) / IM_N;
   const size_t cap = (size_t)(p->num_sms / ncols > 0 ? p->num_sms / ncols : 1);
   dim3 grid((unsigned)(tiles < cap ? tiles : cap), ncols);
-  invmel_tc_kernel<<<grid, 128, smem, st>>>(L);
+  B2D_CUDA(launch_pdl(invmel_tc_kernel, grid, dim3(128), smem, st, L));
   B2D_LAUNCH_CHECK("invmel_tc_kernel");
   return B2D_OK;
 }

@@ -144,8 +144,6 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
     tma::barrier_init(&gbar[0], 1);
     tma::barrier_init(&gbar[1], 1);
     tma::fence_barrier_init();
-    if (nchunks > 0) fetch(0);
-    if (nchunks > 1) fetch(1);
   }
   float w[3][H][3];
   float pb[3];
@@ -161,6 +159,12 @@ __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict_
     }
   }
   for (int i = tid; i < 2 * H * (BINS + 2); i += blockDim.x) (&hp[0][0][0])[i] = 0.f;
+  pdl_wait();  // weights are in registers; gx / hx come from the kernels before (common.cuh: programmatic dependent launch)
+  pdl_trigger();
+  if (tid == 0) {
+    if (nchunks > 0) fetch(0);
+    if (nchunks > 1) fetch(1);
+  }
   __syncthreads();  // also publishes the mbarrier initialisation to every thread
   float h = 0.f;
   if (active) {
@@ -540,8 +544,8 @@ int model_forward(const b2d_model* m, const float* x, float* hx, float* pred, fl
   } else {
     if ((rc = model_encode_mma(m, x, nf, d0, d1, d2, gx, 3, dev_sms, st))) return rc;
   }
-  if (exact_gates) recurrence_kernel<true><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
-  else recurrence_kernel<false><<<B, 96, 0, st>>>(m->d_blob, gx, hx, hseq, T);
+  if (exact_gates) B2D_CUDA(launch_pdl(recurrence_kernel<true>, dim3(B), dim3(96), 0, st, m->d_blob, gx, hx, hseq, T));
+  else B2D_CUDA(launch_pdl(recurrence_kernel<false>, dim3(B), dim3(96), 0, st, m->d_blob, gx, hx, hseq, T));
   B2D_LAUNCH_CHECK("recurrence_kernel");
   if (conv_mode == B2D_CONV_FP32) {
     const int nw = L.total - L.dec_w[0];

@@ -237,6 +237,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decoder_mma_kernel(const float4
     for (int i = lane; i < WARP_FLOATS; i += 32) act[warp * WARP_FLOATS + i] = 0.f;
   __syncthreads();
   um_bulk_wait(&frag_bar);
+  pdl_wait();  // weights and biases staged; activations come from the kernels before (common.cuh: programmatic dependent launch)
+  pdl_trigger();
   float* B0 = act + warp * WARP_FLOATS;  // layer inputs: rows fl * (Lin + 1) + i
   float* B1 = B0 + ROWS0 * S;
   float* B2 = B1 + ROWS1 * S;
@@ -423,6 +425,8 @@ __global__ void __launch_bounds__(EWARPS * 32, 1) encoder_mma_kernel(const float
     for (int i = lane; i < EWARP_FLOATS + 8; i += 32) act[warp * EWARP_FLOATS + i] = 0.f;
   __syncthreads();
   um_bulk_wait(&frag_bar);
+  pdl_wait();
+  pdl_trigger();
   float* X = act + warp * EWARP_FLOATS;
   float* A0 = X + G * EX;            // layer-1 input rows
   float* A1 = A0 + G * ER0 * ES;
@@ -545,7 +549,7 @@ int model_encode_mma(const b2d_model* m, const float* x, size_t nframes, float* 
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma) + (size_t)dfrag_off(4) * 32;
   (void)terms;  // always the fp32-class 3 x TF32 split
   B2D_SMEM_OPT_IN(smem, encoder_mma_kernel<3>);
-  encoder_mma_kernel<3><<<grid, EWARPS * 32, smem, st>>>(fr, m->d_blob, x, nframes, d0, d1, d2, gx);
+  B2D_CUDA(launch_pdl(encoder_mma_kernel<3>, dim3(grid), dim3(EWARPS * 32), smem, st, fr, m->d_blob, x, nframes, d0, d1, d2, gx));
   B2D_LAUNCH_CHECK("encoder_mma_kernel");
   return B2D_OK;
 }
@@ -560,7 +564,8 @@ int model_decode_mma(const b2d_model* m, const float* hseq, const float* d0, con
   const float4* fr = reinterpret_cast<const float4*>(m->d_mma);
   (void)terms;
   B2D_SMEM_OPT_IN(smem, decoder_mma_kernel<3>);
-  decoder_mma_kernel<3><<<grid, WARPS * 32, smem, st>>>(fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel, fused_mode, out_scale);
+  B2D_CUDA(launch_pdl(decoder_mma_kernel<3>, dim3(grid), dim3(WARPS * 32), smem, st, fr, m->d_blob, hseq, d0, d1, d2, x, nframes, pred, mel,
+                      fused_mode, out_scale));
   B2D_LAUNCH_CHECK("decoder_mma_kernel");
   return B2D_OK;
 }

@@ -9,8 +9,9 @@ that seeded construction draws the same initial weights as the reference, but th
 *called*: ``forward`` packs the weights into a native model (Gaussian position channels folded into
 per-position biases) and runs encoder -> persistent recurrence -> decoder kernels.
 
-Inference only (the reference calls the model under ``torch.no_grad()``, app3.py:200, server.py:211);
-CUDA float32 tensors only; no CPU fallback.
+Inference (eval() mode or ``torch.no_grad()``, as the reference calls the model: app3.py:200, server.py:211) runs the fused
+kernels; in train() mode with autograd recording the call is differentiable through hand-written fp32 backward kernels
+(csrc/cell.cu).  CUDA float32 tensors only; no CPU fallback.
 """
 from __future__ import annotations
 
@@ -182,9 +183,43 @@ class GRUUNet2(nn.Module):
             raise ValueError(f"conv_mode must be one of {list(CONV_MODES)}, got {self.conv_mode!r}")
         return CONV_MODES[self.conv_mode] | (0x100 if self.exact_gates else 0)
 
+    def _runner(self):
+        if self._cell_runner is None:
+            from ._cell import ARCH_GRUUNET2, CellRunner
+
+            self._cell_runner = CellRunner(self, ARCH_GRUUNET2)
+        return self._cell_runner
+
+    def _wants_grad(self, *tensors) -> bool:
+        """Training path: the module is in train() mode, autograd is recording, and something asks for a gradient."""
+        return (self.training and torch.is_grad_enabled()
+                and (any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())))
+
     # ---- forward (gruunet2.py:290-306) -------------------------------------------------------
-    @torch.no_grad()
     def forward(self, input: torch.Tensor, hx: Optional[torch.Tensor] = None):
+        """Inference (eval() mode or under ``torch.no_grad()``, as app3.py:200 / server.py:211 call it) runs the fused kernels.
+        In train() mode with autograd recording, the call is differentiable: forward and fp32 backward run on the generic cell
+        kernels (csrc/cell.cu), gradients reach ``input``, ``hx`` and every parameter (server.py:86-142 ``TrainingContext``)."""
+        if self._wants_grad(input, hx):
+            return self._forward_train(input, hx)
+        with torch.no_grad():
+            return self._forward_infer(input, hx)
+
+    def _forward_train(self, input: torch.Tensor, hx: Optional[torch.Tensor]):
+        two_dimmed = input.dim() == 2
+        if two_dimmed:
+            input = input.unsqueeze(0)
+        if input.dim() != 3:
+            raise Exception(f"unknown!! {input.shape}")
+        x = require_cuda_f32(input, "input")
+        shape = (x.shape[0], self.latent_size, self.num_compressed_bins)
+        h0 = torch.zeros(shape, dtype=x.dtype, device=x.device) if hx is None else require_cuda_f32(hx, "hx")
+        if tuple(h0.shape) != shape:
+            raise ValueError(f"hx must be {list(shape)}, got {list(h0.shape)}")
+        out, h = self._runner().forward_autograd(x, h0, None)
+        return (out.squeeze(0) if two_dimmed else out), h
+
+    def _forward_infer(self, input: torch.Tensor, hx: Optional[torch.Tensor] = None):
         two_dimmed = input.dim() == 2
         if two_dimmed:
             input = input.unsqueeze(0)
@@ -201,11 +236,7 @@ class GRUUNet2(nn.Module):
             if tuple(h.shape) != (B, self.latent_size, self.num_compressed_bins):
                 raise ValueError(f"hx must be [{B}, {self.latent_size}, {self.num_compressed_bins}], got {tuple(h.shape)}")
         if not self.uses_tuned_kernels():
-            if self._cell_runner is None:
-                from ._cell import ARCH_GRUUNET2, CellRunner
-
-                self._cell_runner = CellRunner(self, ARCH_GRUUNET2)
-            out = self._cell_runner.forward(x, h)
+            out = self._runner().forward(x, h)
             return (out.squeeze(0) if two_dimmed else out), h
         out = torch.empty_like(x)
         if T == 0:

@@ -70,8 +70,12 @@ class MOMO3(nn.Module):
     def repack(self) -> None:
         self._generation += 1
 
-    @torch.no_grad()
     def forward(self, input: torch.Tensor, hx: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None):
+        """Inference in eval() mode or under ``torch.no_grad()``; differentiable (fp32 backward kernels of csrc/cell.cu) in train()
+        mode with autograd recording.  ``prev`` ([B, 1, n_mels] or [B, n_mels]) is the frame before ``input[:, 0]`` and is treated as a
+        constant, like the reference's detached copy (momo3.py:278, 287)."""
+        train = (self.training and torch.is_grad_enabled()
+                 and (input.requires_grad or (hx is not None and hx.requires_grad) or any(p.requires_grad for p in self.parameters())))
         two_dimmed = input.dim() == 2
         if two_dimmed:
             input = input.unsqueeze(0)
@@ -83,8 +87,13 @@ class MOMO3(nn.Module):
         if hx is None:
             h = torch.zeros(shape, dtype=x.dtype, device=x.device)
         else:
-            h = require_cuda_f32(hx, "hx").clone()
+            h = require_cuda_f32(hx, "hx")
             if tuple(h.shape) != shape:
                 raise ValueError(f"hx must be {list(shape)}, got {list(h.shape)}")
-        out = self._runner.forward(x, h, prev)
+        if train:
+            out, h = self._runner.forward_autograd(x, h, None if prev is None else prev.detach())
+        else:
+            with torch.no_grad():
+                h = h.clone()  # the reference never mutates the caller's hx
+                out = self._runner.forward(x, h, prev)
         return (out.squeeze(0) if two_dimmed else out), h

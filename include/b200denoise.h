@@ -128,6 +128,19 @@ size_t b2d_cell_workspace_bytes(const b2d_cell* cell, int B, int T);
 int b2d_cell_forward(const b2d_cell* cell, const float* x, const float* prev, float* hx, float* out, int B, int T,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fp32 backward of the cell (fine-tuning; server.py:86-142 wraps the module in AdamW) --------
+ * b2d_cell_backward consumes what b2d_cell_forward left in ITS workspace (pass the same buffer, untouched, as forward_workspace)
+ * and the inputs of that forward call (x, prev, the hx the call STARTED from), plus grad_out [B, T, n_mels] and grad_hx_out
+ * [B, hidden[-1], bins] (nullable = zero).  It writes grad_x [B, T, n_mels], grad_hx_in [B, hidden[-1], bins] and grad_params:
+ * b2d_cell_num_param_floats() floats, the gradients of every parameter tensor in state_dict parameters() order and torch
+ * layout, back to back (weights of the Gaussian position channels and biases included).  Deterministic up to the order of the
+ * float atomics that combine per-CTA partial sums. */
+int b2d_cell_num_param_floats(const b2d_cell* cell);
+size_t b2d_cell_backward_workspace_bytes(const b2d_cell* cell, int B, int T);
+int b2d_cell_backward(const b2d_cell* cell, const float* x, const float* prev, const float* hx_in, const void* forward_workspace,
+                      const float* grad_out, const float* grad_hx_out, float* grad_x, float* grad_hx_in, float* grad_params,
+                      int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K0: per-clip peak (app3.py:181-186) ------------------------------------------------------
  * peak[b] = max|wave[b,:]| if > 1e-6 else 1. */
 int b2d_peak(const float* wave, int B, int L, float* peak, void* stream);

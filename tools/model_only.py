@@ -11,7 +11,7 @@ B, T = 256, 126
 sd, cfg = bench.load_model_weights()
 m = adb.GRUUNet2(**cfg)
 m.load_state_dict(sd)
-m = m.to(dev)
+m = m.to(dev).eval()
 x = torch.rand(B, T, 64, device=dev) * 3
 ref = None
 modes = sys.argv[1:] or ["fp32", "mma", "utc"]
