@@ -68,6 +68,12 @@ constexpr int IT_WARPS = 12;                                    // one persisten
 //  CTA-wide shared-memory tables instead of 42 registers fits 128 registers and 14 warps per SM, and is SLOWER: 94.8 us at
 //  12 warps, 96.9 at 13, 91.9 at 14 (B = 256; 281 -> 306 us at B = 1024): +42 LDS.64 per frame cost more than two more
 //  warps give.  tools/tune_gl.py history, gpurun r2.)
+// (Measured, round 2, B = 256 x 126 frames = 1536 runs of 21 frames on 148 x 12 warp slots, 83.5 us: other cuts of the same work
+//  through an experimental run table -- 3 x 22 + 3 x 20 frames per clip with the short runs on the 56 SMs that carry 11 warps
+//  (busiest SM 220 instead of 231 frames): -0.8 %; 5 x 26: +13 %; 4 x 32: +20 %; two rounds of short runs, 9 x 14 ... 21 x 6:
+//  +6 ... +40 %.  A warp needs ~4.0 us per frame with 10 - 12 warps on the SM (3.1 us with 7, 2.9 us with 5), so a launch lasts
+//  as long as its longest run; SM throughput still rises with every added warp (2.61 frames/us/SM at 10.4 warps, 2.94 at 12:
+//  B = 296 fills every slot and reaches 95 % of the HBM roofline figure) and registers cap it at 12.)
 
 // normalised (not yet windowed) sample `is` of interior hop-block js of clip b: the sum of the two partial slots on a run boundary
 __device__ __forceinline__ float partial_sample(const float* __restrict__ part, int b, int R, int n, int js, int is) {
