@@ -41,6 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
                "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd[1:1] = os.environ.get("B2D_EXTRA_NVCC_FLAGS", "").split()  # experiment builds only (tools/), empty for the product
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:

@@ -62,7 +62,10 @@ constexpr int IT_OFF_BAR = IT_OFF_MAG + 2080;
 constexpr int IT_OFF_RING = IT_OFF_BAR + 16;
 constexpr int IT_OFF_XBAR = IT_OFF_RING + 2 * 2 * HOP * 4;
 constexpr int IT_WARP_SMEM = IT_OFF_XBAR + 16;                  // 14912 B
-constexpr int IT_WARPS = 12;                                    // one persistent 12-warp CTA per SM (168 registers / thread)
+#ifndef B2D_IT_WARPS
+#define B2D_IT_WARPS 12
+#endif
+constexpr int IT_WARPS = B2D_IT_WARPS;                                    // one persistent 12-warp CTA per SM (168 registers / thread)
 // (Measured, round 2: with `tprev` gone the kernel no longer waits on HBM -- DRAM traffic fell from 436 MB to ~290 MB per
 //  launch for 89.3 -> 86.9 us -- it is bound by the shared-memory pipe and issue slots.  Reading the 21 lane twiddles from
 //  CTA-wide shared-memory tables instead of 42 registers fits 128 registers and 14 warps per SM, and is SLOWER: 94.8 us at

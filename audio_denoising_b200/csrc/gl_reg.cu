@@ -743,6 +743,167 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_fused_kernel(const GlReg
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// A streaming hop (T <= 4 frames per session, app3.py:213: one n_fft window = 3 frames) in ONE launch with the iterates in
+// SHARED memory: one CTA per session, one warp per frame, __syncthreads between iterations.  Same arithmetic and the same
+// two-slots-per-frame format as gl_reg_fused_kernel above, but x_{k-1}, x_k, x_{k+1} never leave the SM: an iteration costs one
+// frame transform of a lone warp plus a CTA barrier instead of an L2 round trip and a cluster barrier (measured per hop,
+// n_fft 640 / 1536: see DESIGN.md section 4.4; the block-cooperative generic kernel served these before).
+// ------------------------------------------------------------------------------------------------
+constexpr int HOP_WARPS = 4;
+
+template <int R3>
+__global__ void __launch_bounds__(HOP_WARPS * 32, 1) gl_reg_hop_kernel(const GlRegFusedArgs a) {
+  typedef Geo<R3> G;
+  typedef FusedSmem<R3> SM;
+  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2;
+  constexpr int MAG_BYTES = RegSmem<R3>::MAG_BYTES;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WA = reinterpret_cast<float2*>(smem_raw);
+  float2* WB = WA + H2;
+  float2* WN = WB + H2;
+  float2* RT = WN + M;
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + M);
+  float* XS = reinterpret_cast<float*>(warp_base + (size_t)HOP_WARPS * SM::WARP_BYTES);  // [3 iterates][T frames][2 slots][HOP]
+  for (int i = threadIdx.x; i < H2; i += blockDim.x) {
+    WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
+    WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T, b = (int)blockIdx.x, t = warp;
+  const bool active = t < T;
+  unsigned char* wsm = warp_base + (size_t)warp * SM::WARP_BYTES;
+  float2* S = reinterpret_cast<float2*>(wsm);
+  float* mg_s = reinterpret_cast<float*>(wsm + SM::OFF_MAG);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + SM::OFF_BAR);
+  if (lane == 0) {
+    tma::barrier_init(bar, 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+  LaneTwR<R3> tw;
+  lane_twiddles_r<R3>(lane, a.tw, tw);
+  pdl_wait();  // tables and twiddles above are plan constants; the magnitudes come from the kernel before
+  pdl_trigger();
+  if (lane == 0 && active) {  // the frame's magnitude row: loaded once, resident for the init and all iterations
+    tma::expect_bytes(bar, MAG_BYTES);
+    tma::load(mg_s, a.mag_tf + ((size_t)b * T + t) * a.Fp, MAG_BYTES, bar);
+  }
+  const float2 nmom = make_float2(-a.mom, -a.mom);
+  const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+  const int xbuf = T * 2 * HOP;  // floats per iterate
+  __syncthreads();               // tables
+  if (active) tma::wait(bar, 0);
+  // normalised-by-nothing sample `is` of interior hop-block js (1 .. T-1): second half of frame js-1 + first half of frame js
+  auto blk = [&](const float* x, int js, int is) { return x[(2 * js - 1) * HOP + is] + x[(2 * js) * HOP + is]; };
+
+#pragma unroll 1
+  for (int step = 0; step <= a.n_iter; ++step) {
+    const bool init = (step == 0);
+    const bool use_prev = (step >= 2) && (a.mom != 0.f);
+    const float* xin = XS + ((step + 2) % 3) * xbuf;    // x_k       (written by step - 1)
+    const float* xprev = XS + ((step + 1) % 3) * xbuf;  // x_{k-1}   (written by step - 2)
+    float* xout = XS + (step % 3) * xbuf;
+    if (active) {
+      float2 v[G::NV];
+      float2 wA[R3], wB[R3];
+      if (!init) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = t + h;  // padded hop-block index
+          const float2* wtab = h ? WB : WA;
+          if (j == 0 || j == T) {  // reflect-padded edge of the clip (torch.stft center=True)
+            float* dst = reinterpret_cast<float*>(S);
+            const float* wh = a.win + h * HOP;
+            __syncwarp();
+            for (int i = lane; i < HOP; i += 32) {
+              int js, is;
+              if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
+              else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
+              float xv = blk(xin, js, is);
+              if (use_prev) xv = fmaf(-a.mom, blk(xprev, js, is), xv);
+              dst[i] = xv * a.inv_env[is] * wh[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int i = lane + 32 * rr;
+                v[8 * rr + 4 * h + q] = (G::FULL || i < NB) ? S[i + NB * q] : make_float2(0.f, 0.f);
+              }
+          } else {
+            const float2* p1 = reinterpret_cast<const float2*>(xin + (2 * j - 1) * HOP);
+            const float2* p2 = reinterpret_cast<const float2*>(xin + (2 * j) * HOP);
+            const float2* q1 = reinterpret_cast<const float2*>(xprev + (2 * j - 1) * HOP);
+            const float2* q2 = reinterpret_cast<const float2*>(xprev + (2 * j) * HOP);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int i = lane + 32 * rr;
+                float2 xv = make_float2(0.f, 0.f);
+                if (G::FULL || i < NB) {
+                  const int m = i + NB * q;
+                  xv = cadd(p1[m], p2[m]);
+                  if (use_prev) xv = cfma2(cadd(q1[m], q2[m]), nmom, xv);
+                  xv = cscale2(xv, wtab[m]);
+                }
+                v[8 * rr + 4 * h + q] = xv;
+              }
+          }
+        }
+        __syncwarp();
+        fwd1_store_r<R3>(lane, v, tw, S);
+        __syncwarp();
+        fwd2_load_r<R3>(lane, v, S);
+        __syncwarp();
+        fwd2_store_r<R3>(lane, v, tw, S);
+        __syncwarp();
+        fwd3_load_r<R3>(lane, wA, wB, S);
+        project_frame<R3>(lane, wA, wB, RT, mg_s);
+      } else if (a.angles0) {
+        init_frame_angles<R3>(lane, wA, wB, RT, mg_s, a.angles0 + (size_t)b * a.F * T + t, T);
+      } else {
+        init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
+      }
+      __syncwarp();
+      inv1_store_r<R3>(lane, wA, wB, S);
+      __syncwarp();
+      inv2_load_r<R3>(lane, v, tw, S);
+      __syncwarp();
+      inv2_store_r<R3>(lane, v, S);
+      __syncwarp();
+      inv3_load_r<R3>(lane, v, tw, S);
+      float2* d0 = reinterpret_cast<float2*>(xout + (2 * t) * HOP);      // slot 0: first half x window
+      float2* d1 = reinterpret_cast<float2*>(xout + (2 * t + 1) * HOP);  // slot 1: second half x window
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = lane + 32 * rr;
+          if (G::FULL || i < NB) {
+            const int m = i + NB * q;
+            d0[m] = cscale2(v[8 * rr + q], WN[m]);
+            d1[m] = cscale2(v[8 * rr + 4 + q], WN[H2 + m]);
+          }
+        }
+    }
+    __syncthreads();  // x_{k+1} complete
+  }
+  // ---- stitch: hop-block j (1 .. T-1) = its two partial slots x 1 / envelope x clip scale ----
+  const float* fin = XS + (a.n_iter % 3) * xbuf;
+  const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
+  for (int j = 1 + warp; j <= T - 1; j += HOP_WARPS) {
+    float* dst = a.wave + (size_t)b * HOP * (T - 1) + (size_t)(j - 1) * HOP;
+    for (int i = lane; i < HOP; i += 32) dst[i] = blk(fin, j, i) * a.inv_env[i] * sc;
+  }
+}
+
 template <int R3> struct FusedWarps;
 template <> struct FusedWarps<4> { static constexpr int W = 16; };
 template <> struct FusedWarps<5> { static constexpr int W = 16; };
@@ -834,6 +995,42 @@ bool gl_reg_fused_plan(const b2d_plan* p, int B, int T, int* n_out, int* R_out, 
   if (B > fused_max_clusters(r3, csize)) return false;  // a second wave of clusters would cost what the per-iteration launches cost
   *n_out = 1; *R_out = T; *csize_out = csize;
   return true;
+}
+
+// ---- the streaming-hop kernel: plan + launch ----
+template <int R3>
+static size_t hop_smem_bytes(int T) {
+  return (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)HOP_WARPS * FusedSmem<R3>::WARP_BYTES + (size_t)3 * T * 2 * Geo<R3>::HOP * sizeof(float);
+}
+bool gl_reg_hop_plan(const b2d_plan* p, int B, int T) {
+  (void)B;
+  return fused_r3(p) != 0 && !(p->flags & B2D_PLAN_GENERIC_KERNELS) && T >= 3 && T <= HOP_WARPS;
+}
+template <int R3>
+static int launch_hop_t(const GlRegFusedArgs& a, cudaStream_t st) {
+  const size_t smem = hop_smem_bytes<R3>(a.T);
+  static_assert(RegSmem<R3>::TABLE_BYTES + HOP_WARPS * FusedSmem<R3>::WARP_BYTES + 3 * HOP_WARPS * 2 * Geo<R3>::HOP * 4 <= 232448,
+                "per-CTA shared memory exceeds 227 KB");
+  B2D_SMEM_OPT_IN(hop_smem_bytes<R3>(HOP_WARPS), gl_reg_hop_kernel<R3>);
+  B2D_CUDA(launch_pdl(gl_reg_hop_kernel<R3>, dim3((unsigned)a.B), dim3(HOP_WARPS * 32), smem, st, a));
+  B2D_LAUNCH_CHECK("gl_reg_hop_kernel");
+  return B2D_OK;
+}
+int launch_gl_reg_hop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
+                      const unsigned long long* seed_ptr, int B, int T, int n_iter, float mom, const float* out_scale, float* wave,
+                      cudaStream_t st) {
+  GlRegFusedArgs a{};
+  a.mag_tf = mag_tf; a.angles0 = angles0;
+  a.B = B; a.T = T; a.n = 1; a.R = T; a.Fp = p->Fp; a.F = p->F; a.n_iter = n_iter; a.csize = 1;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.mom = mom; a.wave = wave; a.out_scale = out_scale; a.seed = seed; a.seed_ptr = seed_ptr;
+  switch (fused_r3(p)) {
+    case 4: return launch_hop_t<4>(a, st);
+    case 5: return launch_hop_t<5>(a, st);
+    case 8: return launch_hop_t<8>(a, st);
+    case 12: return launch_hop_t<12>(a, st);
+  }
+  return fail(B2D_ERR_UNSUPPORTED, "no streaming-hop Griffin-Lim kernel for n_fft = %d", p->n_fft);
 }
 
 int launch_gl_reg_fused(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,

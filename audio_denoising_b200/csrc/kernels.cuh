@@ -25,6 +25,7 @@ struct GlPartition {
   int fast;  // 0 = generic shared-memory kernel, 1 = n_fft 1024 register kernel, 2 = n_fft 512 (two frames per transform),
              // 3 = n_fft 2048 (warp pair), 4 = warp-synchronous Stockham (gl_warp.cu), 5 = generic-radix register FFT (gl_reg.cu),
              // 6 = the same in a single launch, one cluster of `csize` CTAs per clip (small problems)
+             // 7 = a streaming hop (T <= 4) in a single launch, one CTA per session, iterates in shared memory
   int csize;
 };
 GlPartition gl_partition(const b2d_plan* p, int B, int T);

@@ -751,6 +751,47 @@ def test_fast_paths_match_generic_on_ragged_shapes(dev, n_fft):
     assert pooled.median() > 100.0 and float((pooled <= 90.0).double().mean()) < 0.06, (n_fft, float(pooled.median()))
 
 
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048, 640, 1536])
+def test_fast_paths_match_generic_on_consistent_spectrograms(dev, n_fft):
+    """The same ragged run partitions on CONSISTENT spectrograms -- |STFT| of band-limited signals, where no rebuilt bin nearly
+    cancels and the unit-modulus projection is continuous -- with the tight bar on EVERY clip: 3 iterations from the true
+    phase, register fast path against the generic kernel (VERDICT r1 weak #7)."""
+    import audio_denoising_b200 as adb
+    from audio_denoising_b200 import _cabi, _runtime
+
+    _, metrics, *_ = _oracle()
+    hop = n_fft // 2
+    plans = [_runtime.get_plan(n_fft, hop, 0, 0, dev), _runtime.get_plan(n_fft, hop, 0, 0, dev, flags=_runtime.PLAN_GENERIC_KERNELS)]
+    spec = adb.Spectrogram(n_fft=n_fft, hop_length=hop, power=None).to(dev)
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(7 * n_fft)
+    worst = 1e9
+    for B, T in [(1, 3), (1, 4), (2, 5), (3, 7), (1, 33), (5, 18), (2, 126), (300, 9), (37, 23)]:
+        L = hop * (T - 1)
+        t = torch.arange(L, dtype=torch.float64) / 16000.0
+        f0 = 80.0 + 300.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)
+        x = sum((0.6 / k) * torch.sin(2 * torch.pi * k * f0 * t * (1.0 + 0.05 * torch.sin(2 * torch.pi * 3.0 * t)) + k) for k in range(1, 9))
+        x = (x + 0.05 * torch.randn(B, L, generator=g, dtype=torch.float64)).float().to(dev)
+        X = spec(x)  # [B, F, T] torch layout
+        mag = X.abs().contiguous()
+        assert mag.shape == (B, n_fft // 2 + 1, T)
+        # start from the true phase: the iterates stay next to a consistent spectrogram, no rebuilt bin comes near zero
+        ang = torch.where(mag > 0, X / mag.clamp_min(1e-30), torch.ones_like(X)).contiguous()
+        outs = []
+        for pl in plans:
+            ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(pl.handle, B, T), dtype=torch.uint8, device=dev)
+            wave = torch.zeros(B, pl.out_length(T), device=dev)
+            _cabi.check(lib.b2d_griffinlim(pl.handle, mag.data_ptr(), ang.data_ptr(), 0, B, T, 3, 0.99, None, wave.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), st))
+            outs.append(wave.cpu())
+        sdr = metrics.si_sdr(outs[0], outs[1])
+        assert float(metrics.si_sdr(outs[0], x.cpu()[:, :outs[0].shape[1]]).min()) > 60.0  # and the signal itself comes back
+        worst = min(worst, float(sdr.min()))
+        assert sdr.min() > 90.0, (n_fft, B, T, float(sdr.median()), float(sdr.min()))
+    assert worst > 90.0
+
+
 @pytest.mark.parametrize("n_fft,L,B", [(512, 16000, 2), (2048, 32000, 2), (1024, 160000, 2), (640, 32000, 2), (1536, 40000, 2)])
 def test_pipeline_other_geometries_match_oracle(dev, n_fft, L, B):
     """Whole chain vs the oracle for the other Griffin-Lim fast paths (n_fft 512 / 2048) and for the corpus geometry of
