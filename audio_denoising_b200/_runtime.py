@@ -141,6 +141,19 @@ def draw_seed() -> int:
     return int(torch.randint(1, 2**62, (1,), dtype=torch.int64).item())
 
 
+def derive_seed(base: int, index: int) -> int:
+    """Non-zero 62-bit seed number ``index`` of a stream keyed by ``base`` (splitmix64 finaliser in Python integers, ~1 us): the
+    streaming denoiser draws ``base`` from torch's generator once and derives one seed per hop instead of a ``torch.randint``
+    call (~8 us) on every 16 - 20 ms hop."""
+    x = (base + 0xD1B54A32D192ED03 * (index + 1)) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x & ((1 << 62) - 1)) or 1
+
+
 def is_hann(window_fn, win_length: int, wkwargs=None) -> bool:
     if window_fn is torch.hann_window and not wkwargs:
         return True

@@ -44,9 +44,17 @@ size_t stream_step_ws(const b2d_plan* p, const b2d_model* m, int S) { return str
 __global__ void __launch_bounds__(256) stream_pre_kernel(const float* __restrict__ chunk, const float* __restrict__ win, int N,
                                                          float* __restrict__ x, float* __restrict__ peak) {
   const int s = blockIdx.x;
-  const float* c = chunk + (size_t)s * N;
+  const float* c = chunk + (size_t)s * N;  // may be pinned HOST memory (zero-copy streaming graph): read each sample once
+  constexpr int KEEP = 8;                  // N <= 2048: the chunk stays in registers between the two passes
+  float keep[KEEP];
   float m = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+  for (int q = 0; q < KEEP; ++q) {
+    const int i = threadIdx.x + q * 256;
+    keep[q] = i < N ? c[i] : 0.f;
+    m = fmaxf(m, fabsf(keep[q]));
+  }
+  for (int i = threadIdx.x + KEEP * 256; i < N; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ float red[8];
   __shared__ float pk;
@@ -60,7 +68,12 @@ __global__ void __launch_bounds__(256) stream_pre_kernel(const float* __restrict
   }
   __syncthreads();
   const float p = pk;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) x[(size_t)s * N + i] = (c[i] / p) * win[i];
+#pragma unroll
+  for (int q = 0; q < KEEP; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i < N) x[(size_t)s * N + i] = (keep[q] / p) * win[i];
+  }
+  for (int i = threadIdx.x + KEEP * 256; i < N; i += blockDim.x) x[(size_t)s * N + i] = (c[i] / p) * win[i];
 }
 
 // emit ola[:hop]; shift; ola += y (app3.py:219-224).  N == 2*hop.

@@ -134,8 +134,22 @@ class GRUUNet2(nn.Module):
 
     # ---- native model management -------------------------------------------------------------
     def _signature(self):
-        ps = list(self.parameters()) + list(self.buffers())
-        return (self._generation,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+        # called once per streaming hop: the tensor list is cached (walking the module tree costs ~40 us) and dropped by
+        # everything that can replace a Parameter / buffer object (_apply: .to() / .cuda() / .float(); load_state_dict;
+        # repack()); storage moves and in-place writes show up in (data_ptr, _version)
+        ps = self.__dict__.get("_sig_tensors")
+        if ps is None:
+            ps = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_sig_tensors"] = ps
+        return (self._generation,) + tuple([(p.data_ptr(), p._version) for p in ps])
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_sig_tensors"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_sig_tensors"] = None
+        return super().load_state_dict(*args, **kwargs)
 
     def repack(self) -> None:
         """Force a re-pack on next use.  Needed only after edits autograd cannot see (``p.data.mul_()``, writes through a
@@ -143,6 +157,7 @@ class GRUUNet2(nn.Module):
         automatically."""
         with self._native_lock:
             self._generation += 1
+            self.__dict__["_sig_tensors"] = None
 
     def native_model(self, device: torch.device) -> NativeModel:
         """The packed native model for ``device`` (re-packed after any weight change).  Handles are cached per device

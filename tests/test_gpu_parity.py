@@ -915,9 +915,9 @@ def test_streaming_graph_follows_weight_changes(dev):
         m = adb.GRUUNet2(**cfg)
         m.load_state_dict(states[0])
         m = m.to(dev).eval()
+        torch.manual_seed(0)  # the denoiser draws the base of its per-hop seed stream from torch's generator when it is built
         s = adb.StreamingDenoiser(m, n_fft=640, hop_length=320, n_mels=64, sample_rate=16000, n_iter=4, sessions=1,
                                   angles_fn=None, use_graph=True)
-        torch.manual_seed(0)
         outs = []
         for i in range(6):
             if i == 3 and len(states) > 1:
