@@ -745,17 +745,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_fused_kernel(const GlReg
 
 // ------------------------------------------------------------------------------------------------
 // A streaming hop (T <= 4 frames per session, app3.py:213: one n_fft window = 3 frames) in ONE launch with the iterates in
-// SHARED memory: one CTA per session, one warp per frame, __syncthreads between iterations.  Same arithmetic and the same
-// two-slots-per-frame format as gl_reg_fused_kernel above, but x_{k-1}, x_k, x_{k+1} never leave the SM: an iteration costs one
-// frame transform of a lone warp plus a CTA barrier instead of an L2 round trip and a cluster barrier (measured per hop,
-// n_fft 640 / 1536: see DESIGN.md section 4.4; the block-cooperative generic kernel served these before).
+// SHARED memory: one CTA per session, __syncthreads between iterations.  Same arithmetic and the same two-slots-per-frame
+// format as gl_reg_fused_kernel above, but x_{k-1}, x_k, x_{k+1} never leave the SM, and a frame belongs to a GROUP of
+// NR = ceil(8 R3 / 32) warps: the radix-8 stages 1 and 2 of the forward and inverse transforms are cut by rounds of 32
+// butterflies (gl_reg.cuh), and here every round has its own warp (n_fft 640: 2, n_fft 1536: 3), so a lone frame's critical
+// path is one round per stage instead of NR; the radix-R3 stage and the projection stay on the group's first warp (bin k and
+// its mirror sit in one lane there).  The group's warps meet at a named barrier between the stages.  Bit-identical to the
+// one-warp-per-frame kernels (same butterflies, same order).  Measured per hop: DESIGN.md section 4.4.
 // ------------------------------------------------------------------------------------------------
-constexpr int HOP_WARPS = 4;
+constexpr int HOP_FRAMES = 4;  // frames (warp groups) per CTA
 
 template <int R3>
-__global__ void __launch_bounds__(HOP_WARPS * 32, 1) gl_reg_hop_kernel(const GlRegFusedArgs a) {
+struct HopSmem {  // per frame: exchange buffer (shared by the group's warps) | mag row | mbarrier
   typedef Geo<R3> G;
-  typedef FusedSmem<R3> SM;
+  static constexpr int OFF_MAG = G::XCH * 8;
+  static constexpr int OFF_BAR = OFF_MAG + ((RegSmem<R3>::MAG_BYTES + 15) & ~15);
+  static constexpr int FRAME_BYTES = OFF_BAR + 16;
+};
+
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int R3>
+__global__ void __launch_bounds__(HOP_FRAMES * Geo<R3>::NR * 32, 1) gl_reg_hop_kernel(const GlRegFusedArgs a) {
+  typedef Geo<R3> G;
+  typedef HopSmem<R3> SM;
   constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2;
   constexpr int MAG_BYTES = RegSmem<R3>::MAG_BYTES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -763,8 +778,8 @@ __global__ void __launch_bounds__(HOP_WARPS * 32, 1) gl_reg_hop_kernel(const GlR
   float2* WB = WA + H2;
   float2* WN = WB + H2;
   float2* RT = WN + M;
-  unsigned char* warp_base = reinterpret_cast<unsigned char*>(RT + M);
-  float* XS = reinterpret_cast<float*>(warp_base + (size_t)HOP_WARPS * SM::WARP_BYTES);  // [3 iterates][T frames][2 slots][HOP]
+  unsigned char* frame_base = reinterpret_cast<unsigned char*>(RT + M);
+  float* XS = reinterpret_cast<float*>(frame_base + (size_t)HOP_FRAMES * SM::FRAME_BYTES);  // [3 iterates][T frames][2 slots][HOP]
   for (int i = threadIdx.x; i < H2; i += blockDim.x) {
     WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
     WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
@@ -774,31 +789,40 @@ __global__ void __launch_bounds__(HOP_WARPS * 32, 1) gl_reg_hop_kernel(const GlR
     RT[i] = a.rtw[i];
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = a.T, b = (int)blockIdx.x, t = warp;
+  const int T = a.T, b = (int)blockIdx.x;
+  const int t = warp / NR, r = warp - t * NR;  // this warp's frame and its round of the radix-8 stages
   const bool active = t < T;
-  unsigned char* wsm = warp_base + (size_t)warp * SM::WARP_BYTES;
-  float2* S = reinterpret_cast<float2*>(wsm);
-  float* mg_s = reinterpret_cast<float*>(wsm + SM::OFF_MAG);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + SM::OFF_BAR);
-  if (lane == 0) {
+  const int bar_id = 1 + t;
+  unsigned char* fsm = frame_base + (size_t)t * SM::FRAME_BYTES;
+  float2* S = reinterpret_cast<float2*>(fsm);
+  float* mg_s = reinterpret_cast<float*>(fsm + SM::OFF_MAG);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + SM::OFF_BAR);
+  if (lane == 0 && r == 0) {
     tma::barrier_init(bar, 1);
     tma::fence_barrier_init();
   }
-  __syncwarp();
-  LaneTwR<R3> tw;
-  lane_twiddles_r<R3>(lane, a.tw, tw);
+  // this warp's round: butterflies i = lane + 32 r of stages 1 / 2 (the last round is partial when 8 R3 % 32 != 0)
+  const int i = lane + 32 * r;
+  const bool work = G::FULL || i < NB;
+  const int n3 = (lane >> 3) + 4 * r, k1 = lane & 7;
+  float2 t1[3], t2[3];
+  {
+    const int ii = work ? i : 0, nn = work ? n3 : 0;
+    t1[0] = a.tw[ii]; t1[1] = a.tw[2 * ii]; t1[2] = a.tw[4 * ii];
+    t2[0] = a.tw[8 * nn]; t2[1] = a.tw[16 * nn]; t2[2] = a.tw[32 * nn];
+  }
   pdl_wait();  // tables and twiddles above are plan constants; the magnitudes come from the kernel before
   pdl_trigger();
-  if (lane == 0 && active) {  // the frame's magnitude row: loaded once, resident for the init and all iterations
+  if (lane == 0 && r == 0 && active) {  // the frame's magnitude row: loaded once, resident for the init and all iterations
     tma::expect_bytes(bar, MAG_BYTES);
     tma::load(mg_s, a.mag_tf + ((size_t)b * T + t) * a.Fp, MAG_BYTES, bar);
   }
   const float2 nmom = make_float2(-a.mom, -a.mom);
   const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
   const int xbuf = T * 2 * HOP;  // floats per iterate
-  __syncthreads();               // tables
-  if (active) tma::wait(bar, 0);
-  // normalised-by-nothing sample `is` of interior hop-block js (1 .. T-1): second half of frame js-1 + first half of frame js
+  __syncthreads();               // tables, mbarrier init
+  if (active && r == 0) tma::wait(bar, 0);
+  // sample `is` of interior hop-block js (1 .. T-1): second half of frame js - 1 + first half of frame js
   auto blk = [&](const float* x, int js, int is) { return x[(2 * js - 1) * HOP + is] + x[(2 * js) * HOP + is]; };
 
 #pragma unroll 1
@@ -809,98 +833,128 @@ __global__ void __launch_bounds__(HOP_WARPS * 32, 1) gl_reg_hop_kernel(const GlR
     const float* xprev = XS + ((step + 1) % 3) * xbuf;  // x_{k-1}   (written by step - 2)
     float* xout = XS + (step % 3) * xbuf;
     if (active) {
-      float2 v[G::NV];
-      float2 wA[R3], wB[R3];
+      float2 v[8];
       if (!init) {
+        // ---- stage: v[4 h + q] = windowed (x_k - m x_{k-1})[pair i + NB q of half-block h] ----
+        if (work) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = t + h;  // padded hop-block index
-          const float2* wtab = h ? WB : WA;
-          if (j == 0 || j == T) {  // reflect-padded edge of the clip (torch.stft center=True)
-            float* dst = reinterpret_cast<float*>(S);
-            const float* wh = a.win + h * HOP;
-            __syncwarp();
-            for (int i = lane; i < HOP; i += 32) {
-              int js, is;
-              if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
-              else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-              float xv = blk(xin, js, is);
-              if (use_prev) xv = fmaf(-a.mom, blk(xprev, js, is), xv);
-              dst[i] = xv * a.inv_env[is] * wh[i];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < NR; ++rr)
+          for (int h = 0; h < 2; ++h) {
+            const int j = t + h;  // padded hop-block index
+            const float2* wtab = h ? WB : WA;
+            if (j == 0 || j == T) {  // reflect-padded edge of the clip (torch.stft center=True)
+              const float* wh = a.win + h * HOP;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const int i = lane + 32 * rr;
-                v[8 * rr + 4 * h + q] = (G::FULL || i < NB) ? S[i + NB * q] : make_float2(0.f, 0.f);
-              }
-          } else {
-            const float2* p1 = reinterpret_cast<const float2*>(xin + (2 * j - 1) * HOP);
-            const float2* p2 = reinterpret_cast<const float2*>(xin + (2 * j) * HOP);
-            const float2* q1 = reinterpret_cast<const float2*>(xprev + (2 * j - 1) * HOP);
-            const float2* q2 = reinterpret_cast<const float2*>(xprev + (2 * j) * HOP);
+                float e[2];
 #pragma unroll
-            for (int rr = 0; rr < NR; ++rr)
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int i = lane + 32 * rr;
-                float2 xv = make_float2(0.f, 0.f);
-                if (G::FULL || i < NB) {
-                  const int m = i + NB * q;
-                  xv = cadd(p1[m], p2[m]);
-                  if (use_prev) xv = cfma2(cadd(q1[m], q2[m]), nmom, xv);
-                  xv = cscale2(xv, wtab[m]);
+                for (int c = 0; c < 2; ++c) {
+                  const int idx = 2 * (i + NB * q) + c;
+                  int js, is;
+                  if (j == 0) { js = (idx == 0) ? 2 : 1; is = (idx == 0) ? 0 : HOP - idx; }
+                  else        { js = (idx == HOP - 1) ? T - 2 : T - 1; is = (idx == HOP - 1) ? HOP - 1 : HOP - 2 - idx; }
+                  float xv = blk(xin, js, is);
+                  if (use_prev) xv = fmaf(-a.mom, blk(xprev, js, is), xv);
+                  e[c] = xv * a.inv_env[is] * wh[idx];
                 }
-                v[8 * rr + 4 * h + q] = xv;
+                v[4 * h + q] = make_float2(e[0], e[1]);
               }
+            } else {
+              const float2* p1 = reinterpret_cast<const float2*>(xin + (2 * j - 1) * HOP);
+              const float2* p2 = reinterpret_cast<const float2*>(xin + (2 * j) * HOP);
+              const float2* q1 = reinterpret_cast<const float2*>(xprev + (2 * j - 1) * HOP);
+              const float2* q2 = reinterpret_cast<const float2*>(xprev + (2 * j) * HOP);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int m = i + NB * q;
+                float2 xv = cadd(p1[m], p2[m]);
+                if (use_prev) xv = cfma2(cadd(q1[m], q2[m]), nmom, xv);
+                v[4 * h + q] = cscale2(xv, wtab[m]);
+              }
+            }
           }
+          // ---- forward stage 1: radix 8 over n1, twiddle W_M^{i k1} ----
+          float2 p[8];
+          tw_powers(t1, p);
+          dft8<false>(v);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) S[kk * G::LD1 + i] = kk ? cmul(v[kk], p[kk]) : v[0];
+        }
+        group_sync(bar_id, NR * 32);
+        // ---- forward stage 2: radix 8 over n2, twiddle W_M^{8 n3 k2} ----
+        if (work) {
+#pragma unroll
+          for (int n2 = 0; n2 < 8; ++n2) v[n2] = S[k1 * G::LD1 + R3 * n2 + n3];
+        }
+        group_sync(bar_id, NR * 32);  // S is rewritten in the other layout
+        if (work) {
+          float2 p[8];
+          tw_powers(t2, p);
+          dft8<false>(v);
+#pragma unroll
+          for (int k2 = 0; k2 < 8; ++k2) S[n3 * G::LD2 + k1 + 8 * k2] = k2 ? cmul(v[k2], p[k2]) : v[0];
+        }
+        group_sync(bar_id, NR * 32);
+      }
+      // ---- stage 3 + projection (or the initial spectrum) + inverse stage 3: the group's first warp ----
+      if (r == 0) {
+        float2 wA[R3], wB[R3];
+        if (!init) {
+          fwd3_load_r<R3>(lane, wA, wB, S);
+          project_frame<R3>(lane, wA, wB, RT, mg_s);
+        } else if (a.angles0) {
+          init_frame_angles<R3>(lane, wA, wB, RT, mg_s, a.angles0 + (size_t)b * a.F * T + t, T);
+        } else {
+          init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
         }
         __syncwarp();
-        fwd1_store_r<R3>(lane, v, tw, S);
-        __syncwarp();
-        fwd2_load_r<R3>(lane, v, S);
-        __syncwarp();
-        fwd2_store_r<R3>(lane, v, tw, S);
-        __syncwarp();
-        fwd3_load_r<R3>(lane, wA, wB, S);
-        project_frame<R3>(lane, wA, wB, RT, mg_s);
-      } else if (a.angles0) {
-        init_frame_angles<R3>(lane, wA, wB, RT, mg_s, a.angles0 + (size_t)b * a.F * T + t, T);
-      } else {
-        init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
+        inv1_store_r<R3>(lane, wA, wB, S);
       }
-      __syncwarp();
-      inv1_store_r<R3>(lane, wA, wB, S);
-      __syncwarp();
-      inv2_load_r<R3>(lane, v, tw, S);
-      __syncwarp();
-      inv2_store_r<R3>(lane, v, S);
-      __syncwarp();
-      inv3_load_r<R3>(lane, v, tw, S);
-      float2* d0 = reinterpret_cast<float2*>(xout + (2 * t) * HOP);      // slot 0: first half x window
-      float2* d1 = reinterpret_cast<float2*>(xout + (2 * t + 1) * HOP);  // slot 1: second half x window
+      group_sync(bar_id, NR * 32);
+      // ---- inverse stage 2, stage 1, synthesis window ----
+      if (work) {
+        float2 p[8];
+        tw_powers(t2, p);
 #pragma unroll
-      for (int rr = 0; rr < NR; ++rr)
+        for (int k2 = 0; k2 < 8; ++k2) {
+          const float2 c = S[n3 * G::LD2 + k1 + 8 * k2];
+          v[k2] = k2 ? cmulc(c, p[k2]) : c;
+        }
+        dft8<true>(v);
+      }
+      group_sync(bar_id, NR * 32);  // S is rewritten in the other layout
+      if (work) {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) S[k1 * G::LD1 + R3 * n2 + n3] = v[n2];
+      }
+      group_sync(bar_id, NR * 32);
+      if (work) {
+        float2 p[8];
+        tw_powers(t1, p);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const float2 c = S[kk * G::LD1 + i];
+          v[kk] = kk ? cmulc(c, p[kk]) : c;
+        }
+        dft8<true>(v);
+        float2* d0 = reinterpret_cast<float2*>(xout + (2 * t) * HOP);      // slot 0: first half x window
+        float2* d1 = reinterpret_cast<float2*>(xout + (2 * t + 1) * HOP);  // slot 1: second half x window
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int i = lane + 32 * rr;
-          if (G::FULL || i < NB) {
-            const int m = i + NB * q;
-            d0[m] = cscale2(v[8 * rr + q], WN[m]);
-            d1[m] = cscale2(v[8 * rr + 4 + q], WN[H2 + m]);
-          }
+          const int m = i + NB * q;
+          d0[m] = cscale2(v[q], WN[m]);
+          d1[m] = cscale2(v[4 + q], WN[H2 + m]);
         }
+      }
     }
-    __syncthreads();  // x_{k+1} complete
+    __syncthreads();  // x_{k+1} complete (also fences the exchange buffers for the next step)
   }
   // ---- stitch: hop-block j (1 .. T-1) = its two partial slots x 1 / envelope x clip scale ----
   const float* fin = XS + (a.n_iter % 3) * xbuf;
   const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
-  for (int j = 1 + warp; j <= T - 1; j += HOP_WARPS) {
+  const int nw = (int)blockDim.x >> 5;
+  for (int j = 1 + warp; j <= T - 1; j += nw) {
     float* dst = a.wave + (size_t)b * HOP * (T - 1) + (size_t)(j - 1) * HOP;
-    for (int i = lane; i < HOP; i += 32) dst[i] = blk(fin, j, i) * a.inv_env[i] * sc;
+    for (int q = lane; q < HOP; q += 32) dst[q] = blk(fin, j, q) * a.inv_env[q] * sc;
   }
 }
 
@@ -1000,19 +1054,19 @@ bool gl_reg_fused_plan(const b2d_plan* p, int B, int T, int* n_out, int* R_out, 
 // ---- the streaming-hop kernel: plan + launch ----
 template <int R3>
 static size_t hop_smem_bytes(int T) {
-  return (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)HOP_WARPS * FusedSmem<R3>::WARP_BYTES + (size_t)3 * T * 2 * Geo<R3>::HOP * sizeof(float);
+  return (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)HOP_FRAMES * HopSmem<R3>::FRAME_BYTES + (size_t)3 * T * 2 * Geo<R3>::HOP * sizeof(float);
 }
 bool gl_reg_hop_plan(const b2d_plan* p, int B, int T) {
   (void)B;
-  return fused_r3(p) != 0 && !(p->flags & B2D_PLAN_GENERIC_KERNELS) && T >= 3 && T <= HOP_WARPS;
+  return fused_r3(p) != 0 && !(p->flags & B2D_PLAN_GENERIC_KERNELS) && T >= 3 && T <= HOP_FRAMES;
 }
 template <int R3>
 static int launch_hop_t(const GlRegFusedArgs& a, cudaStream_t st) {
   const size_t smem = hop_smem_bytes<R3>(a.T);
-  static_assert(RegSmem<R3>::TABLE_BYTES + HOP_WARPS * FusedSmem<R3>::WARP_BYTES + 3 * HOP_WARPS * 2 * Geo<R3>::HOP * 4 <= 232448,
+  static_assert(RegSmem<R3>::TABLE_BYTES + HOP_FRAMES * HopSmem<R3>::FRAME_BYTES + 3 * HOP_FRAMES * 2 * Geo<R3>::HOP * 4 <= 232448,
                 "per-CTA shared memory exceeds 227 KB");
-  B2D_SMEM_OPT_IN(hop_smem_bytes<R3>(HOP_WARPS), gl_reg_hop_kernel<R3>);
-  B2D_CUDA(launch_pdl(gl_reg_hop_kernel<R3>, dim3((unsigned)a.B), dim3(HOP_WARPS * 32), smem, st, a));
+  B2D_SMEM_OPT_IN(hop_smem_bytes<R3>(HOP_FRAMES), gl_reg_hop_kernel<R3>);
+  B2D_CUDA(launch_pdl(gl_reg_hop_kernel<R3>, dim3((unsigned)a.B), dim3(HOP_FRAMES * Geo<R3>::NR * 32), smem, st, a));
   B2D_LAUNCH_CHECK("gl_reg_hop_kernel");
   return B2D_OK;
 }
