@@ -122,7 +122,9 @@ def save_checkpoint(name: str, model: GRUUNet2, optimizer=None, scheduler=None, 
 
 class TrainingContext:
     """``TrainingContext`` of server.py:86-142 for the B200 model: wraps the module with AdamW + ExponentialLR(0.9) and restores
-    both from a checkpoint folder.  (Training itself is outside this build: the fused forward has no backward.)"""
+    both from a checkpoint folder.  In ``train()`` mode the wrapped module's forward is differentiable (fp32 backward kernels,
+    csrc/cell.cu), so ``loss.backward(); ctx.optim.step()`` works as it does with the reference module; the training LOOP itself
+    (data, schedule) is the caller's, as in the reference."""
 
     def __init__(self, cls=GRUUNet2, *args, device: Optional[torch.device] = None, **kwargs):
         self.device = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")

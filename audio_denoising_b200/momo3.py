@@ -4,7 +4,7 @@ GRUUNet2's sibling with a first-order delta feature: every frame enters the cell
 (momo3.py:277-283), the Gaussian position channels are appended at the encoder input only (momo3.py:129-148), and the decoder
 has none (momo3.py:160-190).  Same constructor, ``state_dict`` keys / ``parameters()`` order, ``forward(input, hx=None,
 prev=None) -> (out, hx)``, ``hparams`` / ``get_config`` / ``from_config``.  The parameter holders are never called:
-``forward`` runs ``b2d_cell_forward`` (csrc/cell.cu).  Inference only, CUDA float32 only, no CPU fallback.
+``forward`` runs ``b2d_cell_forward`` (csrc/cell.cu).  Inference in eval() / no_grad, differentiable (fp32 backward kernels) in train() mode; CUDA float32 only, no CPU fallback.
 """
 from __future__ import annotations
 
