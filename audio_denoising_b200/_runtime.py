@@ -61,6 +61,7 @@ def melscale_fbanks_htk(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Te
 
 # plan flags (include/b200denoise.h B2D_PLAN_*): fixed at plan creation, nothing on the compute path reads the environment
 PLAN_GENERIC_KERNELS, PLAN_EXACT_SQRT, PLAN_EXACT_UNIT, PLAN_EXACT_PEAK_DIV, PLAN_FP32_INVMEL = 1, 2, 4, 8, 16
+PLAN_CLUSTER_GL = 32
 PLAN_EXACT_ALL = PLAN_EXACT_SQRT | PLAN_EXACT_UNIT | PLAN_EXACT_PEAK_DIV | PLAN_FP32_INVMEL
 
 

@@ -4,6 +4,8 @@
 // run of frames with the overlap-add carry in registers, the momentum term is formed on the time-domain iterates
 // (d = x_k - m x_{k-1}, see gl_fast.cu), the mag row and the hop-blocks of both iterates arrive by TMA one frame ahead, one
 // persistent CTA per SM.  Round 1 ran these lengths on shared-memory Stockham kernels at 19 % / 25 % of HBM peak.
+#include <cooperative_groups.h>
+
 #include "gl_reg.cuh"
 #include "kernels.cuh"
 #include "tma.cuh"
@@ -763,8 +765,9 @@ struct HopSmem {  // per frame: exchange buffer (shared by the group's warps) | 
   static constexpr int FRAME_BYTES = OFF_BAR + 16;
 };
 
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void group_sync(int id, int nthreads) {  // named barriers 1 .. 15; a one-warp group needs none
+  if (nthreads == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int R3>
@@ -958,6 +961,225 @@ __global__ void __launch_bounds__(HOP_FRAMES * Geo<R3>::NR * 32, 1) gl_reg_hop_k
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small and medium problems (one clip ... a few dozen clips) in ONE COOPERATIVE launch over the whole GPU: persistent CTAs,
+// one per SM, each with COOP_GROUPS frame groups of NR warps (a warp per radix-8 round, as in gl_reg_hop_kernel); the frames
+// of all clips are dealt round-robin over the groups of the grid; the iterates live in global memory (L2, ld.global.cg) in
+// the two-slots-per-frame format, and a grid-wide barrier separates the iterations.  (Measured alternative: per-frame progress
+// flags -- st.release after a frame's step, ld.acquire polling of its two or three neighbours before the next -- instead of the
+// grid barrier: 6.8 instead of 5.6 us per iteration for one clip, 12.0 instead of 9.3 us for 16; the release -> poll -> load chain
+// is three dependent L2 round trips.)  The cluster kernel above keeps a clip
+// on 8 - 16 SMs (4 frames per SM sub-partition for a 4 s clip) and the device holds only 8 clusters; here a clip's 126 frames
+// spread over 126 groups on as many SM sub-partitions as there are, and B = 16 clips still fit one wave.
+// ------------------------------------------------------------------------------------------------
+template <int R3> struct CoopGroups { static constexpr int G = 16 / Geo<R3>::NR; };  // 16 warps per CTA (15 at n_fft 1536)
+
+template <int R3>
+__global__ void __launch_bounds__(CoopGroups<R3>::G * Geo<R3>::NR * 32, 1) gl_reg_coop_kernel(const GlRegFusedArgs a) {
+  typedef Geo<R3> G;
+  typedef HopSmem<R3> SM;
+  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2, GROUPS = CoopGroups<R3>::G;
+  constexpr int MAG_BYTES = RegSmem<R3>::MAG_BYTES;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* WA = reinterpret_cast<float2*>(smem_raw);
+  float2* WB = WA + H2;
+  float2* WN = WB + H2;
+  float2* RT = WN + M;
+  unsigned char* frame_base = reinterpret_cast<unsigned char*>(RT + M);
+  for (int i = threadIdx.x; i < H2; i += blockDim.x) {
+    WA[i] = make_float2(a.inv_env[2 * i] * a.win[2 * i], a.inv_env[2 * i + 1] * a.win[2 * i + 1]);
+    WB[i] = make_float2(a.inv_env[2 * i] * a.win[HOP + 2 * i], a.inv_env[2 * i + 1] * a.win[HOP + 2 * i + 1]);
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    WN[i] = make_float2(a.winn[2 * i], a.winn[2 * i + 1]);
+    RT[i] = a.rtw[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;
+  const int g = warp / NR, r = warp - g * NR;  // frame group inside the CTA, round of the radix-8 stages
+  const int bar_id = 1 + g;
+  unsigned char* fsm = frame_base + (size_t)g * SM::FRAME_BYTES;
+  float2* S = reinterpret_cast<float2*>(fsm);
+  float* mg_s = reinterpret_cast<float*>(fsm + SM::OFF_MAG);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + SM::OFF_BAR);
+  if (lane == 0 && r == 0) {
+    tma::barrier_init(bar, 1);
+    tma::fence_barrier_init();
+  }
+  const int i = lane + 32 * r;
+  const bool work = G::FULL || i < NB;
+  const int n3 = (lane >> 3) + 4 * r, k1 = lane & 7;
+  float2 t1[3], t2[3];
+  {
+    const int ii = work ? i : 0, nn = work ? n3 : 0;
+    t1[0] = a.tw[ii]; t1[1] = a.tw[2 * ii]; t1[2] = a.tw[4 * ii];
+    t2[0] = a.tw[8 * nn]; t2[1] = a.tw[16 * nn]; t2[2] = a.tw[32 * nn];
+  }
+  const float2 nmom = make_float2(-a.mom, -a.mom);
+  const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+  const int nframes = a.B * T;
+  // a.csize = groups in use per CTA (the launcher spreads a small problem over all SMs before it fills the groups of any):
+  // groups of one rank across the CTAs first, so a clip's frames sit on as many SMs as possible
+  const int gu = a.csize;
+  const int f0 = g < gu ? ((int)blockIdx.x + g * (int)gridDim.x) : nframes;
+  const int fstep = gu * (int)gridDim.x;
+  const bool resident = f0 + fstep >= nframes;                      // at most one frame for this group: its mag row stays in smem
+  const size_t xclip = (size_t)T * 2 * HOP;                         // floats per clip in an iterate buffer
+  uint32_t uses = 0;
+  __syncthreads();  // tables, mbarrier init
+  if (resident && f0 < nframes && lane == 0 && r == 0) {
+    tma::expect_bytes(bar, MAG_BYTES);
+    tma::load(mg_s, a.mag_tf + (size_t)f0 * a.Fp, MAG_BYTES, bar);
+  }
+  bool mag_ready = false;
+  auto blk = [&](const float* x, int js, int is) { return __ldcg(x + (size_t)(2 * js - 1) * HOP + is) + __ldcg(x + (size_t)(2 * js) * HOP + is); };
+
+#pragma unroll 1
+  for (int step = 0; step <= a.n_iter; ++step) {
+    const bool init = (step == 0);
+    const bool use_prev = (step >= 2) && (a.mom != 0.f);
+#pragma unroll 1
+    for (int f = f0; f < nframes; f += fstep) {
+      const int b = f / T, t = f - b * T;
+      const float* xin = a.x[(step + 2) % 3] + (size_t)b * xclip;    // x_k       (written by step - 1)
+      const float* xprev = a.x[(step + 1) % 3] + (size_t)b * xclip;  // x_{k-1}   (written by step - 2)
+      float* xout = a.x[step % 3] + (size_t)b * xclip;
+      if (!resident && lane == 0 && r == 0) {  // this frame's magnitude row lands while the forward transform runs
+        tma::expect_bytes(bar, MAG_BYTES);
+        tma::load(mg_s, a.mag_tf + (size_t)f * a.Fp, MAG_BYTES, bar);
+      }
+      float2 v[8];
+      if (!init) {
+        if (work) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = t + h;  // padded hop-block index
+            const float2* wtab = h ? WB : WA;
+            if (j == 0 || j == T) {  // reflect-padded edge of the clip (torch.stft center=True)
+              const float* wh = a.win + h * HOP;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float e[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const int idx = 2 * (i + NB * q) + c;
+                  int js, is;
+                  if (j == 0) { js = (idx == 0) ? 2 : 1; is = (idx == 0) ? 0 : HOP - idx; }
+                  else        { js = (idx == HOP - 1) ? T - 2 : T - 1; is = (idx == HOP - 1) ? HOP - 1 : HOP - 2 - idx; }
+                  float xv = blk(xin, js, is);
+                  if (use_prev) xv = fmaf(-a.mom, blk(xprev, js, is), xv);
+                  e[c] = xv * a.inv_env[is] * wh[idx];
+                }
+                v[4 * h + q] = make_float2(e[0], e[1]);
+              }
+            } else {
+              const float2* p1 = reinterpret_cast<const float2*>(xin + (size_t)(2 * j - 1) * HOP);
+              const float2* p2 = reinterpret_cast<const float2*>(xin + (size_t)(2 * j) * HOP);
+              const float2* q1 = reinterpret_cast<const float2*>(xprev + (size_t)(2 * j - 1) * HOP);
+              const float2* q2 = reinterpret_cast<const float2*>(xprev + (size_t)(2 * j) * HOP);
+              float2 xa[4], xb[4], pa[4], pb[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {  // all loads in flight before the first use (L2 round trips)
+                const int m = i + NB * q;
+                xa[q] = __ldcg(p1 + m); xb[q] = __ldcg(p2 + m);
+                if (use_prev) { pa[q] = __ldcg(q1 + m); pb[q] = __ldcg(q2 + m); }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int m = i + NB * q;
+                float2 xv = cadd(xa[q], xb[q]);
+                if (use_prev) xv = cfma2(cadd(pa[q], pb[q]), nmom, xv);
+                v[4 * h + q] = cscale2(xv, wtab[m]);
+              }
+            }
+          }
+          float2 p[8];
+          tw_powers(t1, p);
+          dft8<false>(v);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) S[kk * G::LD1 + i] = kk ? cmul(v[kk], p[kk]) : v[0];
+        }
+        group_sync(bar_id, NR * 32);
+        if (work) {
+#pragma unroll
+          for (int n2 = 0; n2 < 8; ++n2) v[n2] = S[k1 * G::LD1 + R3 * n2 + n3];
+        }
+        group_sync(bar_id, NR * 32);
+        if (work) {
+          float2 p[8];
+          tw_powers(t2, p);
+          dft8<false>(v);
+#pragma unroll
+          for (int k2 = 0; k2 < 8; ++k2) S[n3 * G::LD2 + k1 + 8 * k2] = k2 ? cmul(v[k2], p[k2]) : v[0];
+        }
+        group_sync(bar_id, NR * 32);
+      }
+      if (r == 0) {
+        float2 wA[R3], wB[R3];
+        if (!resident || !mag_ready) { tma::wait(bar, uses & 1); ++uses; mag_ready = true; }
+        if (!init) {
+          fwd3_load_r<R3>(lane, wA, wB, S);
+          project_frame<R3>(lane, wA, wB, RT, mg_s);
+        } else if (a.angles0) {
+          init_frame_angles<R3>(lane, wA, wB, RT, mg_s, a.angles0 + (size_t)b * a.F * T + t, T);
+        } else {
+          init_frame<R3>(lane, wA, wB, RT, mg_s, seed, ((unsigned long long)b * T + t) * (M + 1));
+        }
+        __syncwarp();
+        inv1_store_r<R3>(lane, wA, wB, S);
+      }
+      group_sync(bar_id, NR * 32);
+      if (work) {
+        float2 p[8];
+        tw_powers(t2, p);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          const float2 c = S[n3 * G::LD2 + k1 + 8 * k2];
+          v[k2] = k2 ? cmulc(c, p[k2]) : c;
+        }
+        dft8<true>(v);
+      }
+      group_sync(bar_id, NR * 32);
+      if (work) {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) S[k1 * G::LD1 + R3 * n2 + n3] = v[n2];
+      }
+      group_sync(bar_id, NR * 32);
+      if (work) {
+        float2 p[8];
+        tw_powers(t1, p);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const float2 c = S[kk * G::LD1 + i];
+          v[kk] = kk ? cmulc(c, p[kk]) : c;
+        }
+        dft8<true>(v);
+        float2* d0 = reinterpret_cast<float2*>(xout + (size_t)(2 * t) * HOP);      // slot 0: first half x window
+        float2* d1 = reinterpret_cast<float2*>(xout + (size_t)(2 * t + 1) * HOP);  // slot 1: second half x window
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = i + NB * q;
+          d0[m] = cscale2(v[q], WN[m]);
+          d1[m] = cscale2(v[4 + q], WN[H2 + m]);
+        }
+      }
+      group_sync(bar_id, NR * 32);  // the exchange buffer (and, when not resident, the mag row) is free for the next frame
+    }
+    grid.sync();  // x_{k+1} of every clip complete and visible
+  }
+  // ---- stitch: hop-block j (1 .. T-1) of clip b = its two partial slots x 1 / envelope x clip scale ----
+  const float* fin = a.x[a.n_iter % 3];
+  const int nw = (int)(blockDim.x >> 5) * (int)gridDim.x, gwarp = warp * (int)gridDim.x + (int)blockIdx.x;
+  for (int e = gwarp; e < a.B * (T - 1); e += nw) {
+    const int b = e / (T - 1), j = 1 + e - b * (T - 1);
+    const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
+    float* dst = a.wave + (size_t)b * HOP * (T - 1) + (size_t)(j - 1) * HOP;
+    const float* x = fin + (size_t)b * xclip;
+    for (int q = lane; q < HOP; q += 32) dst[q] = blk(x, j, q) * a.inv_env[q] * sc;
+  }
+}
+
 template <int R3> struct FusedWarps;
 template <> struct FusedWarps<4> { static constexpr int W = 16; };
 template <> struct FusedWarps<5> { static constexpr int W = 16; };
@@ -1085,6 +1307,84 @@ int launch_gl_reg_hop(const b2d_plan* p, const float* mag_tf, const float2* angl
     case 12: return launch_hop_t<12>(a, st);
   }
   return fail(B2D_ERR_UNSUPPORTED, "no streaming-hop Griffin-Lim kernel for n_fft = %d", p->n_fft);
+}
+
+// ---- the cooperative kernel: plan + launch ----
+template <int R3>
+static size_t coop_smem_bytes() { return (size_t)RegSmem<R3>::TABLE_BYTES + (size_t)CoopGroups<R3>::G * HopSmem<R3>::FRAME_BYTES; }
+template <int R3>
+static int coop_max_ctas_t(int num_sms) {  // co-resident CTAs (one per SM when the shared memory fits), queried once
+  static std::atomic<int> cache{0};
+  int v = cache.load();
+  if (v) return v;
+  constexpr int threads = CoopGroups<R3>::G * Geo<R3>::NR * 32;
+  const size_t smem = coop_smem_bytes<R3>();
+  if (cudaFuncSetAttribute(gl_reg_coop_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gl_reg_coop_kernel<R3>, threads, smem) != cudaSuccess) return 0;
+  v = per_sm > 0 ? num_sms : 0;  // one CTA per SM is all the kernel asks for
+  cache.store(v > 0 ? v : -1);
+  return v;
+}
+static int coop_max_ctas(int r3, int num_sms) {
+  int v = 0;
+  switch (r3) {
+    case 4: v = coop_max_ctas_t<4>(num_sms); break;
+    case 5: v = coop_max_ctas_t<5>(num_sms); break;
+    case 8: v = coop_max_ctas_t<8>(num_sms); break;
+    case 12: v = coop_max_ctas_t<12>(num_sms); break;
+  }
+  return v > 0 ? v : 0;
+}
+static int coop_groups(int r3) { return r3 == 4 ? CoopGroups<4>::G : r3 == 5 ? CoopGroups<5>::G : r3 == 8 ? CoopGroups<8>::G : CoopGroups<12>::G; }
+// worth it while a frame group carries at most a few frames per iteration: beyond that the per-iteration batch kernels (TMA rings,
+// register-resident overlap-add) win
+bool gl_reg_coop_plan(const b2d_plan* p, int B, int T) {
+  const int r3 = fused_r3(p);
+  if (!r3 || (p->flags & B2D_PLAN_GENERIC_KERNELS) || T <= HOP_FRAMES) return false;
+  const int ctas = coop_max_ctas(r3, p->num_sms);
+  if (!ctas) return false;
+  return (long)B * T <= 3L * ctas * coop_groups(r3);
+}
+template <int R3>
+static int launch_coop_t(const b2d_plan* p, GlRegFusedArgs a, cudaStream_t st) {
+  constexpr int G = CoopGroups<R3>::G, threads = G * Geo<R3>::NR * 32;
+  const size_t smem = coop_smem_bytes<R3>();
+  static_assert(RegSmem<R3>::TABLE_BYTES + G * HopSmem<R3>::FRAME_BYTES <= 232448, "per-CTA shared memory exceeds 227 KB");
+  B2D_SMEM_OPT_IN(smem, gl_reg_coop_kernel<R3>);
+  const int nframes = a.B * a.T;
+  const int grid = nframes < p->num_sms ? nframes : p->num_sms;
+  int gu = (nframes + grid - 1) / grid;  // frame groups in use per CTA
+  if (gu > G) gu = G;
+  a.csize = gu;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B2D_CUDA(cudaLaunchKernelEx(&cfg, gl_reg_coop_kernel<R3>, a));
+  B2D_LAUNCH_CHECK("gl_reg_coop_kernel");
+  return B2D_OK;
+}
+int launch_gl_reg_coop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
+                       const unsigned long long* seed_ptr, float* x0, float* x1, float* x2, int B, int T, int n_iter,
+                       float mom, const float* out_scale, float* wave, cudaStream_t st) {
+  GlRegFusedArgs a{};
+  a.mag_tf = mag_tf; a.angles0 = angles0; a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
+  a.B = B; a.T = T; a.n = 1; a.R = T; a.Fp = p->Fp; a.F = p->F; a.n_iter = n_iter; a.csize = 1;
+  a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;
+  a.mom = mom; a.wave = wave; a.out_scale = out_scale; a.seed = seed; a.seed_ptr = seed_ptr;
+  switch (fused_r3(p)) {
+    case 4: return launch_coop_t<4>(p, a, st);
+    case 5: return launch_coop_t<5>(p, a, st);
+    case 8: return launch_coop_t<8>(p, a, st);
+    case 12: return launch_coop_t<12>(p, a, st);
+  }
+  return fail(B2D_ERR_UNSUPPORTED, "no cooperative Griffin-Lim kernel for n_fft = %d", p->n_fft);
 }
 
 int launch_gl_reg_fused(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,

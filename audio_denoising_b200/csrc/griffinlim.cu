@@ -292,6 +292,10 @@ int launch_gl_reg_fused(const b2d_plan* p, const float* mag_tf, const float2* an
 int gl_reg_r3(const b2d_plan* p);
 int gl_reg_warps(const b2d_plan* p);
 bool gl_reg_hop_plan(const b2d_plan* p, int B, int T);
+bool gl_reg_coop_plan(const b2d_plan* p, int B, int T);
+int launch_gl_reg_coop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
+                       const unsigned long long* seed_ptr, float* x0, float* x1, float* x2, int B, int T, int n_iter,
+                       float mom, const float* out_scale, float* wave, cudaStream_t st);
 int launch_gl_reg_hop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
                       const unsigned long long* seed_ptr, int B, int T, int n_iter, float mom, const float* out_scale, float* wave,
                       cudaStream_t st);
@@ -319,6 +323,8 @@ GlPartition gl_partition(const b2d_plan* p, int B, int T) {
   q.fast = 0;
   q.csize = 1;
   // small problems (a streaming hop, a handful of clips): init + all iterations in ONE launch, a cluster per clip (gl_reg.cu)
+  // one cooperative launch over the whole GPU, a frame per warp group (gl_reg.cu); B2D_PLAN_CLUSTER_GL keeps the cluster kernel
+  if (!(p->flags & B2D_PLAN_CLUSTER_GL) && gl_reg_coop_plan(p, B, T)) { q.fast = 8; q.n = 1; q.R = T; return q; }
   if (gl_reg_fused_plan(p, B, T, &q.n, &q.R, &q.csize)) { q.fast = 6; return q; }
   // a streaming hop (T = 3 frames): the same in one CTA per session with the iterates in shared memory (gl_reg.cu)
   if (gl_reg_hop_plan(p, B, T)) { q.fast = 7; q.n = 1; q.R = T; return q; }
@@ -371,7 +377,7 @@ static size_t part_floats(const b2d_plan* p, const GlPartition& q, int B) {
 size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   const GlPartition q = gl_partition(p, B, T);
   const size_t pbytes = align_up(part_floats(p, q, B) * sizeof(float), 256);
-  size_t bytes = (q.fast == 7) ? 256 : (q.fast == 1 || q.fast == 5 || q.fast == 6) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
+  size_t bytes = (q.fast == 7) ? 256 : (q.fast == 1 || q.fast == 5 || q.fast == 6 || q.fast == 8) ? 3 * pbytes : 2 * pbytes + align_up((size_t)B * T * p->M * sizeof(float2), 256);
   if (need_mag_copy) bytes += align_up((size_t)B * T * p->Fp * sizeof(float), 256);
   return bytes;
 }
@@ -421,6 +427,9 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   int rc;
   if (q.fast == 7) {
     return launch_gl_reg_hop(p, mag_tf, init_angles, seed, seed_ptr, B, T, n_iter, a.mom, out_scale, wave, st);
+  }
+  if (q.fast == 8) {
+    return launch_gl_reg_coop(p, mag_tf, init_angles, seed, seed_ptr, xa, xb, xc, B, T, n_iter, a.mom, out_scale, wave, st);
   }
   if (q.fast == 6) {
     return launch_gl_reg_fused(p, mag_tf, init_angles, seed, seed_ptr, xa, xb, xc, B, T, q.n, q.R, q.csize, n_iter, a.mom, out_scale, wave, st);

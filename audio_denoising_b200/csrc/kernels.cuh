@@ -26,6 +26,7 @@ struct GlPartition {
              // 3 = n_fft 2048 (warp pair), 4 = warp-synchronous Stockham (gl_warp.cu), 5 = generic-radix register FFT (gl_reg.cu),
              // 6 = the same in a single launch, one cluster of `csize` CTAs per clip (small problems)
              // 7 = a streaming hop (T <= 4) in a single launch, one CTA per session, iterates in shared memory
+             // 8 = small / medium problems in one cooperative launch over the whole GPU (grid barrier between iterations)
   int csize;
 };
 GlPartition gl_partition(const b2d_plan* p, int B, int T);

@@ -74,6 +74,9 @@ int b2d_plan_create(int n_fft, int hop, int n_mels, const float* h_mel_fb, const
 #define B2D_PLAN_EXACT_UNIT 4u
 #define B2D_PLAN_EXACT_PEAK_DIV 8u
 #define B2D_PLAN_FP32_INVMEL 16u
+/* CLUSTER_GL: small problems keep the round-2a single-launch Griffin-Lim (one thread-block cluster per clip, barrier.cluster
+ * between iterations) instead of the cooperative whole-GPU kernel (grid barrier) -- same arithmetic, kept for the tests. */
+#define B2D_PLAN_CLUSTER_GL 32u
 int b2d_plan_create_ex(int n_fft, int hop, int n_mels, const float* h_mel_fb, const float* h_pinv, unsigned flags, b2d_plan** out);
 void b2d_plan_destroy(b2d_plan* plan);
 int b2d_plan_num_frames(const b2d_plan* plan, int L);     /* T = 1 + L / hop                 */

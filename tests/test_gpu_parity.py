@@ -456,6 +456,47 @@ def test_fast_kernels_match_generic_kernels(dev, n_fft, hop):
     assert metrics.rel_l2(dsp.stft(other, n_fft, hop).abs(), mag) < 0.35
 
 
+@pytest.mark.parametrize("n_fft", [512, 640, 1024, 1536])
+def test_single_launch_griffinlim_kernels_agree(dev, n_fft):
+    """The single-launch Griffin-Lim kernels for small problems (csrc/gl_reg.cu): the cooperative whole-GPU kernel (default) against
+    the cluster-per-clip kernel (plan flag CLUSTER_GL) -- same frame arithmetic, same two-slots-per-frame format: BIT-IDENTICAL --
+    and against the per-iteration batch kernels where no cluster plan exists (different association of the overlap-add sums:
+    > 100 dB after a few iterations), seeded in-kernel random initial phase and injected initial angles."""
+    from audio_denoising_b200 import _cabi, _runtime
+
+    _, metrics, *_ = _oracle()
+    hop = n_fft // 2
+    plan_coop = _runtime.get_plan(n_fft, hop, 0, 0, dev)
+    plan_cluster = _runtime.get_plan(n_fft, hop, 0, 0, dev, flags=_runtime.PLAN_CLUSTER_GL)
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(n_fft + 1)
+
+    def run(pl, mag, B, T, n_iter, seed, ang=None):
+        ws = torch.empty(lib.b2d_griffinlim_workspace_bytes(pl.handle, B, T), dtype=torch.uint8, device=dev)
+        wave = torch.zeros(B, pl.out_length(T), device=dev)
+        _cabi.check(lib.b2d_griffinlim_frames(pl.handle, mag.data_ptr(), None if ang is None else ang.data_ptr(), seed, B, T, n_iter, 0.99,
+                                              None, wave.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        return wave.cpu()
+
+    for B, T, exact in [(1, 126, True), (3, 40, True), (2, 9, True), (5, 5, True), (16, 126, False), (24, 31, False)]:
+        mag = (torch.rand(B, T, plan_coop.frame_stride, generator=g) * 2).to(dev)
+        for n_iter, seed in [(0, 11), (1, 11), (5, 12), (4, 0)]:
+            a, b = run(plan_coop, mag, B, T, n_iter, seed), run(plan_cluster, mag, B, T, n_iter, seed)
+            assert torch.isfinite(a).all()
+            if exact:
+                assert torch.equal(a, b), (n_fft, B, T, n_iter, seed, float(metrics.si_sdr(a, b).min()))
+            else:
+                sdr = metrics.si_sdr(a, b)
+                assert sdr.median() > 100.0 and sdr.min() > 40.0, (n_fft, B, T, n_iter, float(sdr.median()), float(sdr.min()))
+        ang = torch.polar(torch.ones(B, n_fft // 2 + 1, T), torch.rand(B, n_fft // 2 + 1, T, generator=g) * 6.28).to(dev).contiguous()
+        a, b = run(plan_coop, mag, B, T, 3, 0, ang), run(plan_cluster, mag, B, T, 3, 0, ang)
+        if exact:
+            assert torch.equal(a, b), (n_fft, B, T, "angles")
+        else:
+            assert metrics.si_sdr(a, b).median() > 100.0
+
+
 def test_rand_init_draws_are_uniform(dev):
     """rand_init=True statistics: with mag == 1 and zero iterations the output is istft(angles_0); its STFT on
     interior frames recovers the projection of the draws, whose mean must match U[0,1) (0.5) closely."""
