@@ -85,21 +85,6 @@ __device__ __forceinline__ float partial_sample(const float* __restrict__ part, 
   if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
   return v;
 }
-// the two reflect-padded edge blocks of a clip (j == 0 and j == T), through a compact non-unrolled loop:
-// dst[i] = (x_k - mom * x_{k-1})[reflected index] * inv_env * win
-__device__ __noinline__ void stage_reflect_block(const float* __restrict__ part, const float* __restrict__ prev, float mom,
-                                                  const float* __restrict__ inv_env, const float* __restrict__ win_half, int b,
-                                                  int R, int n, int T, int j, float* __restrict__ dst, int lane) {
-  for (int i = lane; i < HOP; i += 32) {
-    int js, is;
-    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
-    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-    float v = partial_sample(part, b, R, n, js, is);
-    if (prev) v = fmaf(-mom, partial_sample(prev, b, R, n, js, is), v);
-    dst[i] = v * inv_env[is] * win_half[i];
-  }
-}
-
 // One fused Griffin-Lim iteration (TA:functional/functional.py:316-343) with the momentum term moved to the time domain.
 // The reference forms  angles = rebuilt_k - m * rebuilt_{k-1}  from two complex spectrograms; the STFT is linear, so
 //   rebuilt_k - m * rebuilt_{k-1} = STFT(x_k - m * x_{k-1}),
@@ -192,13 +177,49 @@ __global__ void __launch_bounds__(IT_WARPS * 32, 1) gl_fast512_kernel(const GlFa
       const int j = t + h;            // padded hop-block index
       const int cs = c + h;           // slot inside this run
       const float2* wtab = h ? WB : WA;
-      if (j == 0 || j == T) {          // reflect-padded edge of the clip (2 blocks per clip): generic path via smem
-        __syncwarp();
-        stage_reflect_block(a.xin, USE_PREV ? a.xprev : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, R, n, T, j,
-                            reinterpret_cast<float*>(S), lane);
-        __syncwarp();
+      if (j == 0 || j == T) {
+        // reflect-padded edge of the clip (2 blocks per clip): sample e of the padded block is sample `is` of interior block jsA
+        // read in reverse (one sample comes from block jsB).  Every load is issued before the first use: the launch lasts as
+        // long as its slowest warp, and the two runs per clip that own an edge used to spend ~6 us here in a serial chain of
+        // L2 round trips (16 dependent loop trips with two integer divisions each).
+        const int jsA = (j == 0) ? 1 : T - 1, jsB = (j == 0) ? 2 : T - 2;
+        auto slots = [&](const float* part, int js, const float*& p1, const float*& p2) {  // block js = slot of run (js-1)/n (+ slot 0 of run js/n)
+          const int r1 = (js - 1) / n, r2 = js / n;
+          p1 = part + ((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP;
+          p2 = (r2 != r1) ? part + ((size_t)(b * R + r2) * (n + 1)) * HOP : nullptr;
+        };
+        const float *xa1, *xa2, *xb1, *xb2, *pa1 = nullptr, *pa2 = nullptr, *pb1 = nullptr, *pb2 = nullptr;
+        slots(a.xin, jsA, xa1, xa2);
+        slots(a.xin, jsB, xb1, xb2);
+        if (USE_PREV) { slots(a.xprev, jsA, pa1, pa2); slots(a.xprev, jsB, pb1, pb2); }
+        const float* wh = a.win + h * HOP;
+        float xr[16], pr[16], sc[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[8 * h + q] = S[lane + 32 * q];
+        for (int u = 0; u < 16; ++u) {
+          const int e = 2 * (lane + 32 * (u >> 1)) + (u & 1);
+          const bool odd_one = (j == 0) ? (e == 0) : (e == HOP - 1);  // the one sample that comes from block jsB
+          const int is = (j == 0) ? (e == 0 ? 0 : HOP - e) : (e == HOP - 1 ? HOP - 1 : HOP - 2 - e);
+          const float* s1 = odd_one ? xb1 : xa1;
+          const float* s2 = odd_one ? xb2 : xa2;
+          float x = s1[is];
+          if (s2) x += s2[is];
+          xr[u] = x;
+          if (USE_PREV) {
+            const float* t1 = odd_one ? pb1 : pa1;
+            const float* t2 = odd_one ? pb2 : pa2;
+            float pv = t1[is];
+            if (t2) pv += t2[is];
+            pr[u] = pv;
+          }
+          sc[u] = a.inv_env[is];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = 2 * (lane + 32 * q);
+          float x0 = xr[2 * q], x1 = xr[2 * q + 1];
+          if (USE_PREV) { x0 = fmaf(-a.mom, pr[2 * q], x0); x1 = fmaf(-a.mom, pr[2 * q + 1], x1); }
+          v[8 * h + q] = make_float2(x0 * sc[2 * q] * wh[e], x1 * sc[2 * q + 1] * wh[e + 1]);
+        }
       } else if (cs >= 1 && cs <= nrun - 1) {  // interior block of this run: already in the shared-memory ring
         if (h == 1) {  // (h == 0: the same block was awaited one frame ago)
           if (cs & 1) { mbar_wait(xbar + 1, xuse1 & 1); ++xuse1; } else { mbar_wait(xbar, xuse0 & 1); ++xuse0; }

@@ -375,4 +375,65 @@ B2D_HD void quad_special(float2& E0, float2& E256, float2& O0, float2& O256, flo
 }
 
 }  // namespace fast512
+#ifdef __CUDACC__
+// reflect-padded edge block of a clip (j == 0 or j == T): dst[i] = (x_k - mom x_{k-1})[reflected index] * inv_env * win
+// (prev == nullptr: no momentum term; win_half == nullptr: no window).
+// Sample i of the padded block is sample `is` of interior block jsA read in reverse (one sample comes from block jsB); the slot
+// pointers are resolved once and the loads of 8 samples per lane are all in flight before the first use: a launch lasts as long
+// as its slowest warp, and the two runs per clip that own an edge used to spend a serial chain of HOP / 32 L2 round trips here.
+template <int HOP>
+__device__ __forceinline__ void stage_reflect_wide(const float* part, const float* prev, float mom, const float* __restrict__ inv_env,
+                                                  const float* __restrict__ win_half, int b, int R, int n, int T, int j,
+                                                  float* __restrict__ dst, int lane) {
+  const int jsA = (j == 0) ? 1 : T - 1, jsB = (j == 0) ? 2 : T - 2;
+  auto slots = [&](const float* x, int js, const float*& p1, const float*& p2) {  // block js = slot of run (js-1)/n (+ slot 0 of run js/n)
+    const int r1 = (js - 1) / n, r2 = js / n;
+    p1 = x + ((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP;
+    p2 = (r2 != r1) ? x + ((size_t)(b * R + r2) * (n + 1)) * HOP : nullptr;
+  };
+  const float *xa1, *xa2, *xb1, *xb2, *pa1 = nullptr, *pa2 = nullptr, *pb1 = nullptr, *pb2 = nullptr;
+  slots(part, jsA, xa1, xa2);
+  slots(part, jsB, xb1, xb2);
+  if (prev) { slots(prev, jsA, pa1, pa2); slots(prev, jsB, pb1, pb2); }
+  constexpr int PER = HOP / 32, CH = 8;
+  static_assert(HOP % 32 == 0, "hop must be a multiple of the warp size");
+#pragma unroll 1
+  for (int q0 = 0; q0 < PER; q0 += CH) {
+    float xr[CH], pr[CH], sc[CH];
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+      const int i = lane + 32 * (q0 + u);
+      xr[u] = 0.f; pr[u] = 0.f; sc[u] = 0.f;
+      if (q0 + u < PER) {
+        const bool odd_one = (j == 0) ? (i == 0) : (i == HOP - 1);
+        const int is = (j == 0) ? (i == 0 ? 0 : HOP - i) : (i == HOP - 1 ? HOP - 1 : HOP - 2 - i);
+        const float* s1 = odd_one ? xb1 : xa1;
+        const float* s2 = odd_one ? xb2 : xa2;
+        float x = __ldcg(s1 + is);
+        if (s2) x += __ldcg(s2 + is);
+        xr[u] = x;
+        if (prev) {
+          const float* t1 = odd_one ? pb1 : pa1;
+          const float* t2 = odd_one ? pb2 : pa2;
+          float pv = __ldcg(t1 + is);
+          if (t2) pv += __ldcg(t2 + is);
+          pr[u] = pv;
+        }
+        sc[u] = inv_env[is];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+      const int i = lane + 32 * (q0 + u);
+      if (q0 + u < PER) {
+        float x = xr[u];
+        if (prev) x = fmaf(-mom, pr[u], x);
+        dst[i] = win_half ? x * sc[u] * win_half[i] : x * sc[u];
+      }
+    }
+  }
+}
+
+#endif
+
 }  // namespace b2d

@@ -79,21 +79,6 @@ __device__ __forceinline__ void n20_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// reflect-padded edge block of a clip (j == 0 or j == T): envelope-normalised, windowed samples
-__device__ __noinline__ void n20_stage_reflect(const float* part, const float* __restrict__ inv_env, const float* __restrict__ win_half,
-                                               int b, int R, int n, int T, int j, float* __restrict__ dst, int lane) {
-  constexpr int HOP = n2048::HOP2;
-  for (int i = lane; i < HOP; i += 32) {
-    int js, is;
-    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
-    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-    const int r1 = (js - 1) / n, r2 = js / n;
-    float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
-    if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
-    dst[i] = v * inv_env[is] * win_half[i];
-  }
-}
-
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 template <bool USE_PREV, bool INIT>
@@ -186,7 +171,7 @@ __global__ void __launch_bounds__(n2048::PAIRS * 64, 1) gl_fast_n2048_kernel(con
         const float2* wtab = (h ? WB : WA) + odd * 256;
         if (j == 0 || j == T) {  // reflect-padded edge of the clip: generic path through this warp's exchange buffer
           __syncwarp();
-          n20_stage_reflect(a.xin, a.inv_env, a.win + h * HOP2, b, R, n, T, j, reinterpret_cast<float*>(S), lane);
+          stage_reflect_wide<HOP2>(a.xin, nullptr, 0.f, a.inv_env, a.win + h * HOP2, b, R, n, T, j, reinterpret_cast<float*>(S), lane);
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 8; ++q) v[8 * h + q] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(S) + 4 * (lane + 32 * q) + sub);

@@ -62,21 +62,6 @@ __device__ __forceinline__ void n5_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// reflect-padded edge block of a clip (j == 0 or j == T): envelope-normalised samples, no window
-__device__ __noinline__ void n5_stage_reflect(const float* part, const float* __restrict__ inv_env, int b, int R, int n, int T, int j,
-                                              float* __restrict__ dst, int lane) {
-  constexpr int HOP = n512::HOPN;
-  for (int i = lane; i < HOP; i += 32) {
-    int js, is;
-    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
-    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-    const int r1 = (js - 1) / n, r2 = js / n;
-    float v = part[((size_t)(b * R + r1) * (n + 1) + (js - r1 * n)) * HOP + is];
-    if (r2 != r1) v += part[((size_t)(b * R + r2) * (n + 1)) * HOP + is];
-    dst[i] = v * inv_env[is];
-  }
-}
-
 template <bool USE_PREV>
 __global__ void __launch_bounds__(n512::WARPS * 32, 1) gl_fast_n512_kernel(const GlN512Args a) {
   using namespace n512;
@@ -139,7 +124,7 @@ __global__ void __launch_bounds__(n512::WARPS * 32, 1) gl_fast_n512_kernel(const
     auto load_block = [&](int j, int slot, float* x) {  // envelope-normalised samples lane + 32 q of padded hop-block j
       if (j == 0 || j == T) {
         __syncwarp();
-        n5_stage_reflect(a.xin, a.inv_env, b, R, n, T, j, Sf, lane);
+        stage_reflect_wide<HOPN>(a.xin, nullptr, 0.f, a.inv_env, nullptr, b, R, n, T, j, Sf, lane);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) x[q] = Sf[lane + 32 * q];

@@ -55,20 +55,6 @@ __device__ __forceinline__ float reg_partial_sample(const float* part, int b, in
   if (r2 != r1) v += __ldcg(part + ((size_t)(b * R + r2) * (n + 1)) * HOP + is);
   return v;
 }
-template <int HOP>
-__device__ __noinline__ void reg_stage_reflect(const float* part, const float* prev, float mom,
-                                               const float* __restrict__ inv_env, const float* __restrict__ win_half, int b, int R,
-                                               int n, int T, int j, float* __restrict__ dst, int lane) {
-  for (int i = lane; i < HOP; i += 32) {
-    int js, is;
-    if (j == 0) { js = (i == 0) ? 2 : 1; is = (i == 0) ? 0 : HOP - i; }
-    else        { js = (i == HOP - 1) ? T - 2 : T - 1; is = (i == HOP - 1) ? HOP - 1 : HOP - 2 - i; }
-    float v = reg_partial_sample<HOP>(part, b, R, n, js, is);
-    if (prev) v = fmaf(-mom, reg_partial_sample<HOP>(prev, b, R, n, js, is), v);
-    dst[i] = v * inv_env[is] * win_half[i];
-  }
-}
-
 template <int R3, int WARPS, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_kernel(const GlRegArgs a) {
   constexpr bool USE_PREV = (MODE == MODE_ITER);
@@ -153,7 +139,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gl_reg_kernel(const GlRegArgs a
         const float2* wtab = h ? WB : WA;
         if (j == 0 || j == T) {  // reflect-padded edge of the clip
           __syncwarp();
-          reg_stage_reflect<HOP>(a.xin, USE_PREV ? a.xprev : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, R, n, T, j,
+          stage_reflect_wide<HOP>(a.xin, USE_PREV ? a.xprev : nullptr, a.mom, a.inv_env, a.win + h * HOP, b, R, n, T, j,
                                  reinterpret_cast<float*>(S), lane);
           __syncwarp();
 #pragma unroll
