@@ -144,14 +144,18 @@ B2D_HD void dft5(float2* v) {
 }
 
 // Counter-based uniform draw for the Griffin-Lim initial angles (rand_init=True, TA:functional/functional.py:310
-// draws real and imaginary parts ~ U[0,1)): splitmix64 of (seed, element index) -> two 24-bit mantissas.
+// draws real and imaginary parts ~ U[0,1)): two 24-bit mantissas from (seed, element index) through 32-bit multiply-xorshift
+// rounds (the `lowbias32` constants).  (Round 1 used splitmix64: its three 64-bit multiplies cost ~45 integer instructions per
+// draw on a GPU without a 64-bit multiplier -- as much as the inverse FFT of the init kernels beside it.)
 B2D_HD float2 rand_angle(unsigned long long seed, unsigned long long idx) {
-  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27; x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
+  unsigned a = (unsigned)idx * 0x9E3779B9u + (unsigned)seed;
+  unsigned b = ((unsigned)(idx >> 32) + 0x7F4A7C15u) * 0x85EBCA6Bu + (unsigned)(seed >> 32);
+  a ^= b;
+  a ^= a >> 16; a *= 0x21F0AAADu; a ^= a >> 15; a *= 0x735A2D97u; a ^= a >> 15;
+  b += a * 0x9E3779B9u;
+  b ^= b >> 16; b *= 0x21F0AAADu; b ^= b >> 15; b *= 0x735A2D97u; b ^= b >> 15;
   const float k = 1.0f / 16777216.0f;
-  return make_float2((float)((unsigned)(x >> 40)) * k, (float)((unsigned)(x >> 8) & 0xFFFFFFu) * k);
+  return make_float2((float)(a >> 8) * k, (float)(b >> 8) * k);
 }
 
 // One radix-R Stockham butterfly: work item w in [0, rows * M/R) of a pass over `rows` independent

@@ -343,7 +343,7 @@ struct GlInitArgs {
 };
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const GlInitArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS > 8 ? 1 : 2)) gl_fast512_init_kernel(const GlInitArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* WN = reinterpret_cast<float2*>(smem_raw);
   float2* RT = WN + 512;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * WARPS + warp;
+  const int gw = blockIdx.x * (int)(blockDim.x >> 5) + warp;  // CTAs of blockDim.x / 32 <= WARPS warps
   if (gw >= a.B * a.R) return;
   const int b = gw / a.R, r = gw - b * a.R;
   const int n = a.n, R = a.R, T = a.T;
@@ -432,17 +432,26 @@ __global__ void __launch_bounds__(WARPS * 32, 2) gl_fast512_init_kernel(const Gl
   for (int q = 0; q < 8; ++q) dst[lane + 32 * q] = carry[q];
 }
 
+template <int WMAX>  // kernel instantiated for CTAs of up to WMAX warps, launched with `warps` of them
+static int launch_init_w(const GlInitArgs& a, int warps, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * 1024 + (size_t)warps * WARP_SMEM;
+  B2D_SMEM_OPT_IN(sizeof(float2) * 1024 + (size_t)WMAX * WARP_SMEM, gl_fast512_init_kernel<WMAX>);
+  B2D_CUDA(launch_pdl(gl_fast512_init_kernel<WMAX>, dim3((a.B * a.R + warps - 1) / warps), dim3(warps * 32), smem, st, a));
+  B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
+  return B2D_OK;
+}
+
 int launch_gl_fast512_init(const b2d_plan* p, const float* mag_tf, float* xout, int B, int T, int n, int R, unsigned long long seed,
                            const unsigned long long* seed_ptr, cudaStream_t st) {
   GlInitArgs a;
   a.mag_tf = mag_tf; a.xout = xout; a.B = B; a.T = T; a.n = n; a.R = R; a.Fp = p->Fp;
   a.tw512 = p->d_tw512; a.rtw = p->d_rtw; a.winn = p->d_winn; a.seed = seed; a.seed_ptr = seed_ptr;
-  constexpr int W = 8;
-  const size_t smem = sizeof(float2) * 1024 + (size_t)W * WARP_SMEM;
-  B2D_SMEM_OPT_IN(smem, gl_fast512_init_kernel<W>);
-  B2D_CUDA(launch_pdl(gl_fast512_init_kernel<W>, dim3((B * R + W - 1) / W), dim3(W * 32), smem, st, a));
-  B2D_LAUNCH_CHECK("gl_fast512_init_kernel");
-  return B2D_OK;
+  // a launch lasts as long as its busiest SM: when the runs fit one CTA per SM, size the CTAs so that they do (config 2: 1536 runs
+  // = 140 CTAs of 11 warps instead of 192 CTAs of 8, which put 16 warps on 44 of the 148 SMs and 8 on the rest)
+  const int runs = B * R;
+  const int per_sm = (runs + p->num_sms - 1) / p->num_sms;
+  if (per_sm > 8 && per_sm <= 12) return launch_init_w<12>(a, per_sm, st);
+  return launch_init_w<8>(a, 8, st);
 }
 
 // ------------------------------------------------------------------------------------------------
