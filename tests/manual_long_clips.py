@@ -7,10 +7,10 @@ from audio_denoising_b200 import _cabi, _runtime
 from oracle import metrics
 dev = torch.device("cuda:0"); lib = _cabi.lib(); st = torch.cuda.current_stream().cuda_stream
 g = torch.Generator().manual_seed(1)
-for n_fft in (512, 1024, 2048):
+for n_fft in (512, 640, 1024, 1536, 2048):
     plan = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev)
     plan_g = _runtime.get_plan(n_fft, n_fft // 2, 0, 0, dev, flags=_runtime.PLAN_GENERIC_KERNELS)
-    for B, T in [(2, 3126), (1, 18751), (3000, 4)]:
+    for B, T in [(2, 3126), (1, 18751), (3000, 4), (3000, 3), (28, 126), (29, 126), (1, 5), (400, 9)]:
         mag = (torch.rand(B, T, plan.frame_stride, generator=g) * 2).to(dev)
         outs = []
         for pl in (plan, plan_g):
