@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(512) stft_kernel(const StftArgs a) {
   const int p = N / 2;
   const FastDiv d_M(M), d_half(M / 2 + 1), d_mel(a.n_mels > 0 ? a.n_mels : 1);  // index math without integer division (fft.cuh)
   const float* x = a.wave + (size_t)b * a.L;
-  const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
-
   for (int i = threadIdx.x; i < M; i += blockDim.x) tw_s[i] = a.tw[i];
+  pdl_wait();  // the twiddle table is a plan constant; the waveform and the scale come from the kernels before
+  pdl_trigger();
+  const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
   const int padded = a.L + 2 * p;
   for (int i = threadIdx.x; i < xlen; i += blockDim.x) {
     const int c = t0 * hop + i;
@@ -459,16 +460,16 @@ int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, in
   const int threads = ((long)grid.x * grid.y <= 2 * p->num_sms) ? 512 : 256;
   if (p->M == 320) {
     B2D_SMEM_OPT_IN(smem, stft_kernel<320>);
-    stft_kernel<320><<<grid, threads, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(stft_kernel<320>, grid, dim3(threads), smem, st, a));
   } else if (p->M == 512) {
     B2D_SMEM_OPT_IN(smem, stft_kernel<512>);
-    stft_kernel<512><<<grid, threads, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(stft_kernel<512>, grid, dim3(threads), smem, st, a));
   } else if (p->M == 768) {
     B2D_SMEM_OPT_IN(smem, stft_kernel<768>);
-    stft_kernel<768><<<grid, threads, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(stft_kernel<768>, grid, dim3(threads), smem, st, a));
   } else {
     B2D_SMEM_OPT_IN(smem, stft_kernel<0>);
-    stft_kernel<0><<<grid, threads, smem, st>>>(a);
+    B2D_CUDA(launch_pdl(stft_kernel<0>, grid, dim3(threads), smem, st, a));
   }
   B2D_LAUNCH_CHECK("stft_kernel");
   return B2D_OK;

@@ -44,6 +44,8 @@ size_t stream_step_ws(const b2d_plan* p, const b2d_model* m, int S) { return str
 __global__ void __launch_bounds__(256) stream_pre_kernel(const float* __restrict__ chunk, const float* __restrict__ win, int N,
                                                          float* __restrict__ x, float* __restrict__ peak) {
   const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
   const float* c = chunk + (size_t)s * N;  // may be pinned HOST memory (zero-copy streaming graph): read each sample once
   constexpr int KEEP = 8;                  // N <= 2048: the chunk stays in registers between the two passes
   float keep[KEEP];
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) stream_ola_kernel(const float* __restrict
                                                          float* __restrict__ out, int hop) {
   const int s = blockIdx.x;
   const int N = 2 * hop;
+  pdl_wait();  // y comes from the Griffin-Lim kernel before
+  pdl_trigger();
   for (int i = threadIdx.x; i < hop; i += blockDim.x) {
     const float o0 = ola[(size_t)s * N + i], o1 = ola[(size_t)s * N + hop + i];
     out[(size_t)s * hop + i] = o0;
@@ -100,7 +104,7 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
   B2D_REQUIRE(ws_bytes >= w.total, B2D_ERR_WORKSPACE, "stream workspace too small (%zu < %zu)", ws_bytes, w.total);
   const int N = p->n_fft, T = 3;
   int rc;
-  stream_pre_kernel<<<S, 256, 0, st>>>(chunk, p->d_win, N, w.x, w.peak);
+  B2D_CUDA(launch_pdl(stream_pre_kernel, dim3(S), dim3(256), 0, st, chunk, p->d_win, N, w.x, w.peak));
   B2D_LAUNCH_CHECK("stream_pre_kernel");
   if ((rc = launch_stft(p, w.x, nullptr, S, N, w.logmel, nullptr, nullptr, st))) return rc;
   if ((rc = model_forward(m, w.logmel, hx, w.pred, w.mel, 1, 0.f, S, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
@@ -110,7 +114,7 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
     return rc;
   }
   if ((rc = gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st, d_seed))) return rc;
-  stream_ola_kernel<<<S, 256, 0, st>>>(w.y, ola, out, p->hop);
+  B2D_CUDA(launch_pdl(stream_ola_kernel, dim3(S), dim3(256), 0, st, w.y, ola, out, p->hop));
   B2D_LAUNCH_CHECK("stream_ola_kernel");
   return B2D_OK;
 }
