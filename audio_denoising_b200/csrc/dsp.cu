@@ -122,6 +122,10 @@ struct StftArgs {
   float2* spec;      // [B,F,T] or null
   float* logmel_bt;  // [B,T,n_mels] or null
   float* logmel_bm;  // [B,n_mels,T] or null
+  // streaming hop (stream.cu): the chunk conditioning of app3.py:179-188 fused in -- wave = (chunk / peak) * win with
+  // peak[b] = max|chunk[b]| (1 when <= 1e-6), written to pre_peak; one CTA per session (T <= G), wave is not read
+  const float* pre_chunk;  // [B, L] raw chunk (device or pinned host memory) or null
+  float* pre_peak;         // [B]
 };
 
 // MT: complex transform length known at compile time (fft_rows_t: 320 / 512 / 768) or 0
@@ -145,6 +149,30 @@ __global__ void __launch_bounds__(512) stft_kernel(const StftArgs a) {
   pdl_wait();  // the twiddle table is a plan constant; the waveform and the scale come from the kernels before
   pdl_trigger();
   const float sc = a.inv_scale ? a.inv_scale[b] : 1.0f;
+  float* raw = reinterpret_cast<float*>(bufB);  // pre mode: the raw chunk (L <= 2 G M floats), read once from (possibly host) memory
+  float pk = 1.0f;
+  if (a.pre_chunk) {
+    __shared__ float red[32];
+    __shared__ float pk_s;
+    const float* c = a.pre_chunk + (size_t)b * a.L;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < a.L; i += blockDim.x) {
+      const float v = c[i];
+      raw[i] = v;
+      m = fmaxf(m, fabsf(v));
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = red[0];
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) v = fmaxf(v, red[i]);
+      pk_s = (v > 1e-6f) ? v : 1.0f;
+      a.pre_peak[b] = pk_s;
+    }
+    __syncthreads();
+    pk = pk_s;
+  }
   const int padded = a.L + 2 * p;
   for (int i = threadIdx.x; i < xlen; i += blockDim.x) {
     const int c = t0 * hop + i;
@@ -153,7 +181,7 @@ __global__ void __launch_bounds__(512) stft_kernel(const StftArgs a) {
       int s = c - p;
       if (s < 0) s = -s;
       if (s >= a.L) s = 2 * (a.L - 1) - s;
-      v = x[s] / sc;
+      v = a.pre_chunk ? (raw[s] / pk) * a.win[s] : x[s] / sc;
     }
     xin[i] = v;
   }
@@ -415,6 +443,7 @@ __global__ void __launch_bounds__(256) to_frame_layout_kernel(const float* __res
 // host launchers
 // ------------------------------------------------------------------------------------------------
 static int frames_per_block(const b2d_plan* p) { return p->M <= 1024 ? 4 : 2; }
+int stft_frames_per_block(const b2d_plan* p) { return frames_per_block(p); }
 
 int launch_peak(const float* wave, int B, int L, float* peak, float* partial, int chunks, cudaStream_t st) {
   peak_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(wave, L, chunks, partial);
@@ -439,7 +468,8 @@ bool stft_reg_supported(const b2d_plan* p, int B, int L);  // gl_reg.cu
 int launch_stft_reg(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt, cudaStream_t st);
 
 int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, int B, int L, float* logmel_bt,
-                float* logmel_bm, float2* spec, cudaStream_t st) {
+                float* logmel_bm, float2* spec, cudaStream_t st, float* pre_peak) {
+  if (pre_peak) goto generic;  // streaming hop with the chunk conditioning fused in: block-cooperative kernel, one CTA per session
   if (p->n_fft == 1024 && p->hop == 512 && logmel_bt && !logmel_bm && !spec && L >= 1024 && p->n_mels <= 128 && p->mel_seg_pad <= 320 && (long long)B * (1 + L / p->hop) < (1ll << 30) &&
       !(p->flags & B2D_PLAN_GENERIC_KERNELS))
     return launch_stft_fast512(p, wave, inv_scale, B, L, logmel_bt, st);
@@ -447,12 +477,18 @@ int launch_stft(const b2d_plan* p, const float* wave, const float* inv_scale, in
   if (logmel_bt && !logmel_bm && !spec && !(p->flags & B2D_PLAN_GENERIC_KERNELS) && stft_reg_supported(p, B, L) &&
       (long long)B * (1 + L / p->hop) >= 64)
     return launch_stft_reg(p, wave, inv_scale, B, L, logmel_bt, st);
+generic:
   StftArgs a;
   a.wave = wave; a.inv_scale = inv_scale; a.B = B; a.L = L; a.T = 1 + L / p->hop; a.G = frames_per_block(p);
   a.n_fft = p->n_fft; a.hop = p->hop; a.M = p->M; a.F = p->F; a.n_mels = p->n_mels; a.fd = p->fft;
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win;
   a.mel_lo = p->d_mel_lo; a.mel_cnt = p->d_mel_cnt; a.mel_off = p->d_mel_off; a.mel_w = p->d_mel_w;
   a.spec = spec; a.logmel_bt = logmel_bt; a.logmel_bm = logmel_bm;
+  a.pre_chunk = nullptr; a.pre_peak = nullptr;
+  if (pre_peak) {  // streaming hop: `wave` is the raw chunk, conditioning fused in (one CTA per session)
+    B2D_REQUIRE(L == p->n_fft && a.T <= a.G && !inv_scale, B2D_ERR_UNSUPPORTED, "fused chunk conditioning needs one n_fft window per session");
+    a.pre_chunk = wave; a.pre_peak = pre_peak;
+  }
   const int xlen = (a.G - 1) * p->hop + p->n_fft;
   const size_t smem = sizeof(float2) * (size_t)(p->M + 2 * a.G * p->M) + sizeof(float) * (size_t)(xlen + a.G * (p->M + 1)) + 16;
   dim3 grid((a.T + a.G - 1) / a.G, B);

@@ -572,6 +572,10 @@ struct GlRegFusedArgs {
   const float* out_scale;   // [B] or null
   unsigned long long seed;
   const unsigned long long* seed_ptr;
+  // streaming hop only (gl_reg_hop_kernel, T == 3): overlap-add ring update fused behind the last iteration (app3.py:219-224):
+  // hop_out[s] = ola[s][:hop]; ola[s] = [ola[s][hop:] + y[:hop], y[hop:]] with y = the hop's 2 * hop output samples; wave unused
+  float* ola;               // [B, 2 * HOP] or null
+  float* hop_out;           // [B, HOP]
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -941,6 +945,18 @@ __global__ void __launch_bounds__(HOP_FRAMES * Geo<R3>::NR * 32, 1) gl_reg_hop_k
   const float* fin = XS + (a.n_iter % 3) * xbuf;
   const float sc = a.out_scale ? a.out_scale[b] : 1.0f;
   const int nw = (int)blockDim.x >> 5;
+  if (a.ola != nullptr) {  // T == 3: y = hop-blocks 1 and 2; emit the ring's first half, shift, add
+    float* ring = a.ola + (size_t)b * 2 * HOP;
+    float* out = a.hop_out + (size_t)b * HOP;
+    for (int q = threadIdx.x; q < HOP; q += blockDim.x) {
+      const float y0 = blk(fin, 1, q) * a.inv_env[q] * sc, y1 = blk(fin, 2, q) * a.inv_env[q] * sc;
+      const float o0 = ring[q], o1 = ring[HOP + q];
+      out[q] = o0;
+      ring[q] = o1 + y0;
+      ring[HOP + q] = y1;
+    }
+    return;
+  }
   for (int j = 1 + warp; j <= T - 1; j += nw) {
     float* dst = a.wave + (size_t)b * HOP * (T - 1) + (size_t)(j - 1) * HOP;
     for (int q = lane; q < HOP; q += 32) dst[q] = blk(fin, j, q) * a.inv_env[q] * sc;
@@ -1280,8 +1296,10 @@ static int launch_hop_t(const GlRegFusedArgs& a, cudaStream_t st) {
 }
 int launch_gl_reg_hop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
                       const unsigned long long* seed_ptr, int B, int T, int n_iter, float mom, const float* out_scale, float* wave,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* ola, float* hop_out) {
   GlRegFusedArgs a{};
+  B2D_REQUIRE(ola == nullptr || (T == 3 && hop_out != nullptr), B2D_ERR_BAD_ARG, "fused overlap-add needs a 3-frame hop and an output buffer");
+  a.ola = ola; a.hop_out = hop_out;
   a.mag_tf = mag_tf; a.angles0 = angles0;
   a.B = B; a.T = T; a.n = 1; a.R = T; a.Fp = p->Fp; a.F = p->F; a.n_iter = n_iter; a.csize = 1;
   a.tw = p->d_tw; a.rtw = p->d_rtw; a.win = p->d_win; a.winn = p->d_winn; a.inv_env = p->d_inv_env;

@@ -298,7 +298,7 @@ int launch_gl_reg_coop(const b2d_plan* p, const float* mag_tf, const float2* ang
                        float mom, const float* out_scale, float* wave, cudaStream_t st);
 int launch_gl_reg_hop(const b2d_plan* p, const float* mag_tf, const float2* angles0, unsigned long long seed,
                       const unsigned long long* seed_ptr, int B, int T, int n_iter, float mom, const float* out_scale, float* wave,
-                      cudaStream_t st);
+                      cudaStream_t st, float* ola, float* hop_out);
 
 // uniform cut for the generic shared-memory kernel: one CTA per run, runs a multiple of G frames long
 static GlPartition generic_partition(const b2d_plan* p, int B, int T) {
@@ -382,9 +382,11 @@ size_t gl_workspace_bytes(const b2d_plan* p, int B, int T, bool need_mag_copy) {
   return bytes;
 }
 
+bool gl_fuses_ola(const b2d_plan* p, int B, int T) { return T == 3 && gl_partition(p, B, T).fast == 7; }
+
 int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, unsigned long long seed, int B, int T, int n_iter,
            float momentum, const float* out_scale, float* wave, void* ws, size_t ws_bytes, cudaStream_t st,
-           const unsigned long long* seed_ptr) {
+           const unsigned long long* seed_ptr, float* ola, float* hop_out) {
   B2D_REQUIRE(p->hop * 2 == p->n_fft, B2D_ERR_UNSUPPORTED, "Griffin-Lim requires hop == n_fft/2 (got n_fft=%d hop=%d)", p->n_fft, p->hop);
   B2D_REQUIRE(T >= 3, B2D_ERR_BAD_ARG, "Griffin-Lim needs at least 3 frames (got %d)", T);
   B2D_REQUIRE(momentum >= 0.f && momentum < 1.f, B2D_ERR_BAD_ARG, "momentum must be in range [0, 1). Found: %g", (double)momentum);
@@ -426,7 +428,7 @@ int gl_run(const b2d_plan* p, const float* mag_tf, const float2* init_angles, un
   bool direct_interior = false;
   int rc;
   if (q.fast == 7) {
-    return launch_gl_reg_hop(p, mag_tf, init_angles, seed, seed_ptr, B, T, n_iter, a.mom, out_scale, wave, st);
+    return launch_gl_reg_hop(p, mag_tf, init_angles, seed, seed_ptr, B, T, n_iter, a.mom, out_scale, wave, st, ola, hop_out);
   }
   if (q.fast == 8) {
     return launch_gl_reg_coop(p, mag_tf, init_angles, seed, seed_ptr, xa, xb, xc, B, T, n_iter, a.mom, out_scale, wave, st);

@@ -104,15 +104,22 @@ int stream_step_impl(const b2d_plan* p, const b2d_model* m, const float* chunk, 
   B2D_REQUIRE(ws_bytes >= w.total, B2D_ERR_WORKSPACE, "stream workspace too small (%zu < %zu)", ws_bytes, w.total);
   const int N = p->n_fft, T = 3;
   int rc;
-  B2D_CUDA(launch_pdl(stream_pre_kernel, dim3(S), dim3(256), 0, st, chunk, p->d_win, N, w.x, w.peak));
-  B2D_LAUNCH_CHECK("stream_pre_kernel");
-  if ((rc = launch_stft(p, w.x, nullptr, S, N, w.logmel, nullptr, nullptr, st))) return rc;
+  if (stft_frames_per_block(p) >= T) {
+    // peak normalise + Hann pre-window fused into the STFT kernel (one CTA per session reads the chunk once, possibly from pinned host memory)
+    if ((rc = launch_stft(p, chunk, nullptr, S, N, w.logmel, nullptr, nullptr, st, w.peak))) return rc;
+  } else {
+    B2D_CUDA(launch_pdl(stream_pre_kernel, dim3(S), dim3(256), 0, st, chunk, p->d_win, N, w.x, w.peak));
+    B2D_LAUNCH_CHECK("stream_pre_kernel");
+    if ((rc = launch_stft(p, w.x, nullptr, S, N, w.logmel, nullptr, nullptr, st))) return rc;
+  }
   if ((rc = model_forward(m, w.logmel, hx, w.pred, w.mel, 1, 0.f, S, T, conv_mode, w.model_ws, w.model_bytes, st))) return rc;
   if (p->d_tw8 != nullptr && !(p->flags & B2D_PLAN_FP32_INVMEL)) {
     if ((rc = launch_inverse_mel_tc(p, w.mel, (size_t)S * T, w.mag, 3, st))) return rc;
   } else if ((rc = launch_inverse_mel(p, w.mel, S, T, w.mag, false, st))) {
     return rc;
   }
+  if (gl_fuses_ola(p, S, T))  // emit + shift + add of the overlap-add ring behind the last iteration of the single-launch hop kernel
+    return gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st, d_seed, ola, out);
   if ((rc = gl_run(p, w.mag, init_angles, seed, S, T, n_iter, momentum, w.peak, w.y, w.gl_ws, w.gl_bytes, st, d_seed))) return rc;
   B2D_CUDA(launch_pdl(stream_ola_kernel, dim3(S), dim3(256), 0, st, w.y, ola, out, p->hop));
   B2D_LAUNCH_CHECK("stream_ola_kernel");
