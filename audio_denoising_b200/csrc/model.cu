@@ -120,6 +120,12 @@ __device__ __forceinline__ float tanhf_(float v) { return EXACT ? tanhf(v) : 1.0
 // shared-memory ring, two chunks ahead of the step that consumes them.  (Round 1 prefetched one step ahead with plain loads:
 // a step is shorter than an L2 round trip, so every step waited for its gates -- 0.58 us per step.)
 constexpr int REC_CHUNK = 8;
+// (Measured, round 2 -- ncu on this kernel at B = 256: 231 warp instructions per warp and step (204 of them the 51 LDS + 153 FMA
+//  of the three gates), issue slots 44 % busy with two CTAs = 6 warps per SM: the step is bound by the instructions the two
+//  resident clips issue, not by one warp's latency.  Two restructurings were built, bit-identical, and dropped: (a) 4 warps =
+//  bins, lane = channel, the three taps as one float4 broadcast LDS.128 + packed FMAs (119 instead of 204 instructions per
+//  thread-step, but 254 registers and 8-way bank conflicts on the tap stores): 66 us, no gain; (b) a warp per (gate, bin), 12
+//  warps, two barriers per step: 139 us -- 60 % more instructions per clip-step at 17 of 32 lanes busy.)
 
 template <bool EXACT>
 __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict__ blob, const float* __restrict__ gx,
