@@ -238,3 +238,17 @@ def test_momo3_dropin_state_dict_and_interface():
         m(torch.zeros(1, 2, 24))
     g = adb.GRUUNet2(4, 1, (8, 12), (3, 5), (2, 2), (1, 2))
     assert not g.uses_tuned_kernels() and adb.GRUUNet2(4, 1, (17,) * 4, (3,) * 4, (2,) * 4, (1,) * 4).uses_tuned_kernels()
+
+
+def test_derived_seed_stream_is_nonzero_62_bit_and_decorrelated():
+    """_runtime.derive_seed: the per-hop seeds of the streaming denoiser (one torch draw per denoiser, splitmix64 per hop)."""
+    from audio_denoising_b200._runtime import derive_seed
+
+    seeds = [derive_seed(0x1234_5678_9ABC, k) for k in range(4096)]
+    assert len(set(seeds)) == len(seeds) and all(0 < s < 2 ** 62 for s in seeds)
+    assert derive_seed(0x1234_5678_9ABC, 7) == seeds[7]  # a pure function of (base, index)
+    assert derive_seed(0x1234_5678_9ABD, 7) != seeds[7]
+    # consecutive seeds differ in about half of their bits (no counter-like structure reaches the in-kernel hash)
+    flips = [bin(a ^ b).count("1") for a, b in zip(seeds, seeds[1:])]
+    assert 26 < sum(flips) / len(flips) < 36
+    assert derive_seed(0, 0) != 0
