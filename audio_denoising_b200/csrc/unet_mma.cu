@@ -215,6 +215,14 @@ __device__ __forceinline__ void prefetch_range(const float* p, int bytes, int la
   for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p) + o));
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS) and its group bookkeeping
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int TERMS>
 __global__ void __launch_bounds__(WARPS * 32, 1) decoder_mma_kernel(const float4* __restrict__ frags, const float* __restrict__ blob,
                                                                     const float* __restrict__ hseq, const float* __restrict__ d0,
@@ -259,34 +267,74 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decoder_mma_kernel(const float4
       prefetch_range(x + fn * NMEL, G * NMEL * 4, lane);
     }
     // ---- stage everything this frame pair needs (all loads are independent: one exposed latency per iteration) ----------
+    // Every input element goes global -> shared memory with a 4-byte cp.async (the [channel][position] -> [position][channel]
+    // transpose happens in the destination address), in four commit groups in the order the layers need them: the hidden
+    // state before layer 0, skip d2 before layer 1, d1 before layer 2, d0 -- half of the bytes -- before the last layer.  Only
+    // the first group's latency is exposed; round 1 staged everything with loads + stores up front (ncu: long_scoreboard 1.3 per issue).
     for (int e = lane; e < G * HS; e += 32) {
       const int fl = e / HS, r = e - fl * HS, ch = r >> 2, i = r & 3;
-      B0[(fl * 5 + i) * S + ch] = fl < nf ? hseq[(f0 + fl) * HS + r] : 0.f;
+      float* dst = &B0[(fl * 5 + i) * S + ch];
+      if (fl < nf) cp_async4(dst, hseq + (f0 + fl) * HS + r); else *dst = 0.f;
     }
+    cp_async_commit();
 #pragma unroll
     for (int fl = 0; fl < G; ++fl) {
       const bool live = fl < nf;
       const float* s2 = d2 + (f0 + fl) * D2;
+#pragma unroll
+      for (int cg = 0; cg < 5; ++cg) {
+        const int ch = 4 * cg + sc;
+        if (ch < H) {
+          float* dst = &B1[(fl * 9 + si) * S + H + ch];
+          if (live) cp_async4(dst, s2 + ch * 8 + si); else *dst = 0.f;
+        }
+      }
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int fl = 0; fl < G; ++fl) {
+      const bool live = fl < nf;
       const float* s1 = d1 + (f0 + fl) * D1;
+#pragma unroll
+      for (int cg = 0; cg < 5; ++cg) {
+        const int ch = 4 * cg + sc;
+        if (ch < H) {
+#pragma unroll
+          for (int pg = 0; pg < 2; ++pg) {
+            float* dst = &B2[(fl * 17 + 8 * pg + si) * S + H + ch];
+            if (live) cp_async4(dst, s1 + ch * 16 + 8 * pg + si); else *dst = 0.f;
+          }
+        }
+      }
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int fl = 0; fl < G; ++fl) {
+      const bool live = fl < nf;
       const float* s0 = d0 + (f0 + fl) * D0;
 #pragma unroll
       for (int cg = 0; cg < 5; ++cg) {
         const int ch = 4 * cg + sc;
         if (ch < H) {
-          B1[(fl * 9 + si) * S + H + ch] = live ? s2[ch * 8 + si] : 0.f;
 #pragma unroll
-          for (int pg = 0; pg < 2; ++pg) B2[(fl * 17 + 8 * pg + si) * S + H + ch] = live ? s1[ch * 16 + 8 * pg + si] : 0.f;
-#pragma unroll
-          for (int pg = 0; pg < 4; ++pg) B3[(fl * 33 + 8 * pg + si) * S + H + ch] = live ? s0[ch * 32 + 8 * pg + si] : 0.f;
+          for (int pg = 0; pg < 4; ++pg) {
+            float* dst = &B3[(fl * 33 + 8 * pg + si) * S + H + ch];
+            if (live) cp_async4(dst, s0 + ch * 32 + 8 * pg + si); else *dst = 0.f;
+          }
         }
       }
     }
+    cp_async_commit();
+    cp_async_wait<3>();
     __syncwarp();
     up_layer<4, 3, 1, TERMS>(B0, B1, FR + dfrag_off(0) * 32, PB + dpb_off(0), 0, lane);
+    cp_async_wait<2>();
     __syncwarp();
     up_layer<8, 5, 1, TERMS>(B1, B2, FR + dfrag_off(1) * 32, PB + dpb_off(1), 0, lane);
+    cp_async_wait<1>();
     __syncwarp();
     up_layer<16, 5, 2, TERMS>(B2, B3, FR + dfrag_off(2) * 32, PB + dpb_off(2), 0, lane);
+    cp_async_wait<0>();
     __syncwarp();
     last_layer<4, TERMS>(B3, OUT, FR + dfrag_off(3) * 32, PB + dpb_off(3), lane);
     __syncwarp();
@@ -432,6 +480,8 @@ __global__ void __launch_bounds__(EWARPS * 32, 1) encoder_mma_kernel(const float
   float* A1 = A0 + G * ER0 * ES;
   float* A2 = A1 + G * ER1 * ES;
   const size_t stride = (size_t)gridDim.x * EWARPS * G;
+  // (Measured, round 2: the input frames of trip k + 1 by cp.async into a second X buffer while trip k computes: 99 us instead of
+  //  98 us -- the L2 prefetch below already hides that latency; the same idea is worth 23 us in the decoder, whose inputs are 18 x larger.)
   for (size_t f0 = ((size_t)blockIdx.x * EWARPS + warp) * G; f0 < nframes; f0 += stride) {
     const int nf = (int)min((size_t)G, nframes - f0);
     if (f0 + stride + G <= nframes) prefetch_range(x + (f0 + stride) * NMEL, G * NMEL * 4, lane);
