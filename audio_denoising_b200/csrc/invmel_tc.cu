@@ -274,10 +274,12 @@ static void put_image(std::vector<float>& img, size_t base, int NP, int KP, int 
   img[base + (size_t)NP * KP + canon_off_f(n, k, KP)] = tf32_big(w - big);
 }
 
-// plan: inverse-mel weight images (3 column slices of [176, 64], big | small each)
+// plan: inverse-mel weight images (ceil(Fp / 176) column slices of [176, 64], big | small each; 3 slices at n_fft 1024, 5 at 1536)
 int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv) {
-  if (p->n_mels != IM_K || p->Fp > 3 * IM_N) { p->d_tw8 = nullptr; return B2D_OK; }  // only the 64-mel, n_fft <= 1048 shape
-  std::vector<float> img((size_t)3 * 2 * IM_N * IM_K, 0.f);
+  constexpr int kMaxSlices = 12;  // n_fft <= 4096: Fp = 2052 <= 12 x 176
+  const int nslices = (p->Fp + IM_N - 1) / IM_N;
+  if (p->n_mels != IM_K || nslices > kMaxSlices) { p->d_tw8 = nullptr; return B2D_OK; }  // 64 mel bins only
+  std::vector<float> img((size_t)nslices * 2 * IM_N * IM_K, 0.f);
   for (int f = 0; f < p->F; ++f) {
     const int col = f / IM_N, n = f - col * IM_N;
     for (int k = 0; k < IM_K; ++k) put_image(img, (size_t)col * 2 * IM_N * IM_K, IM_N, IM_K, n, k, h_pinv[(size_t)f * IM_K + k]);
@@ -290,7 +292,7 @@ int plan_pack_invmel_tc(b2d_plan* p, const float* h_pinv) {
 }
 
 int launch_inverse_mel_tc(const b2d_plan* p, const float* mel_bt, size_t nframes, float* mag_tf, int terms, cudaStream_t st) {
-  B2D_REQUIRE(p->d_tw8 != nullptr, B2D_ERR_UNSUPPORTED, "tensor-core inverse mel needs n_mels == 64 and n_fft <= 1048");
+  B2D_REQUIRE(p->d_tw8 != nullptr, B2D_ERR_UNSUPPORTED, "tensor-core inverse mel needs n_mels == 64");
   TcInvMel L;
   L.mel = mel_bt; L.wimg = reinterpret_cast<const float*>(p->d_tw8); L.out = mag_tf; L.nframes = nframes; L.Fp = p->Fp; L.terms = terms;
   const size_t smem = sizeof(float) * (size_t)(4 * 128 * IM_K + 2 * IM_N * IM_K) + 64;  // two A buffers (big | small) + the weight images
