@@ -1,5 +1,5 @@
-"""The reference-native geometry (app3.py:29-33: 48 kHz, n_fft 1536, hop 768) in batch mode: this path runs on the generic
-shared-memory STFT / Griffin-Lim kernels (no register fast path for M = 768 yet), the model and inverse mel as usual."""
+"""The reference-native geometry (app3.py:29-33: 48 kHz, n_fft 1536, hop 768) and the 16 kHz / n_fft 640 geometry of BASELINE
+config 3 in batch mode: register-FFT STFT / Griffin-Lim kernels (gl_reg.cu), tensor-core model and inverse mel."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
