@@ -125,7 +125,9 @@ constexpr int REC_CHUNK = 8;
 //  resident clips issue, not by one warp's latency.  Two restructurings were built, bit-identical, and dropped: (a) 4 warps =
 //  bins, lane = channel, the three taps as one float4 broadcast LDS.128 + packed FMAs (119 instead of 204 instructions per
 //  thread-step, but 254 registers and 8-way bank conflicts on the tap stores): 66 us, no gain; (b) a warp per (gate, bin), 12
-//  warps, two barriers per step: 139 us -- 60 % more instructions per clip-step at 17 of 32 lanes busy.)
+//  warps, two barriers per step: 139 us -- 60 % more instructions per clip-step at 17 of 32 lanes busy; (c) this layout with every
+//  hidden value stored twice so that one LDS.64 feeds a packed FMA for the reset / update sums (159 instead of 204 instructions):
+//  75 us and 255 registers with spills -- the packed FMA does not issue at the scalar rate here.)
 
 template <bool EXACT>
 __global__ void __launch_bounds__(96) recurrence_kernel(const float* __restrict__ blob, const float* __restrict__ gx,
