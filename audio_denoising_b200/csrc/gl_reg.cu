@@ -980,7 +980,7 @@ template <int R3>
 __global__ void __launch_bounds__(CoopGroups<R3>::G * Geo<R3>::NR * 32, 1) gl_reg_coop_kernel(const GlRegFusedArgs a) {
   typedef Geo<R3> G;
   typedef HopSmem<R3> SM;
-  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2, GROUPS = CoopGroups<R3>::G;
+  constexpr int M = G::M, HOP = G::HOP, NB = G::NB, NR = G::NR, H2 = M / 2;
   constexpr int MAG_BYTES = RegSmem<R3>::MAG_BYTES;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];

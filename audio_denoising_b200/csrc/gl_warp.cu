@@ -99,7 +99,7 @@ __device__ __forceinline__ float gw_block_sample(const float* part, const float*
 template <bool USE_PREV>
 __global__ void __launch_bounds__(512, 1) gl_warp_kernel(const GlWarpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int M = a.M, hop = a.M, N = 2 * a.M, T = a.T, n = a.n, R = a.R;
+  const int M = a.M, hop = a.M, T = a.T, n = a.n, R = a.R;
   float2* tw_s = reinterpret_cast<float2*>(smem_raw);  // [M] shared by the CTA
   const size_t wbytes = (size_t)28 * M + (((size_t)a.Fp * 4 + 15) & ~(size_t)15) + 16;  // bufA | bufB | tprev row | carry | mag row | mbarrier
   unsigned char* wbase = smem_raw + (size_t)8 * M;
